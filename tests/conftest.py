@@ -1,0 +1,36 @@
+"""pytest configuration: `gpu` marker + repo root on sys.path.
+
+`-m "not gpu"` runs on the CPU-only build container (oracle vs golden vectors, host logic,
+C-ABI symbol checks, gloo world_size-2 tests); `-m gpu` runs on a B200 and calls the CUDA
+path through the C-ABI.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "reference: needs the read-only reference tree (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    has_gpu = torch.cuda.is_available()
+    skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords and not has_gpu:
+            item.add_marker(skip_gpu)
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN

@@ -1,0 +1,180 @@
+/*
+ * quadsim.h -- C ABI of libquadsim.so, the B200 (sm_100a) batched WaypointQuadEnv simulator.
+ *
+ * The reference (LahiruCooray/rl-aerial-manipulator) has no FFI: its hot path sits behind two
+ * Python protocols, gymnasium.Env (the reference class) and Stable-Baselines3 VecEnv (what drives
+ * it).  The entry points below are what a binding for that path needs; each one names the reference
+ * interface it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every buffer is CALLER-OWNED DEVICE memory (e.g. torch CUDA tensors' data_ptr()), except where a
+ *     parameter is documented as host memory; the handle owns only the per-env hidden state pool;
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and return immediately;
+ *   - every function returns 0 on success or a negative QS_E* code; the text of the last error of a
+ *     handle (or of the library, for a NULL handle) is returned by qs_last_error();
+ *   - no C++ exceptions cross this boundary; one handle must not be used from two threads at once.
+ */
+#ifndef QUADSIM_H
+#define QUADSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_ABI_VERSION 1
+
+/* error codes */
+#define QS_OK 0
+#define QS_EINVAL (-1)  /* bad argument / unsupported configuration */
+#define QS_ECUDA (-2)   /* a CUDA runtime call failed; see qs_last_error() */
+#define QS_ENOMEM (-3)
+
+/* qs_config.precision */
+#define QS_F32 0
+#define QS_F64 1
+/* qs_config.integrator */
+#define QS_RK4 0    /* fixed-step classical RK4, `substeps` sub-intervals per 5 ms env step (throughput mode) */
+#define QS_LSODA 1  /* per-env port of ODEPACK LSODA's Adams path == scipy.integrate.odeint defaults (parity mode, f64) */
+
+/* bits of the per-env flags byte written by qs_step / qs_rollout_step */
+#define QS_FLAG_TERMINATED 0x01
+#define QS_FLAG_TRUNCATED 0x02   /* the reference's `truncated` return value (may be set together with TERMINATED) */
+#define QS_FLAG_SUCCESS 0x04     /* info['success'] is True  */
+#define QS_FLAG_STOPPED 0x08     /* info['stopped'] is True  */
+#define QS_FLAG_CRASHED 0x10     /* info['crashed']          */
+#define QS_FLAG_OOB 0x20         /* info['out_of_bounds']    */
+#define QS_FLAG_LSODA_FAIL 0x80  /* LSODA mode only: the integrator hit a condition the port does not cover */
+
+#define QS_ACT_DIM 4
+#define QS_STATE_DIM 13
+#define QS_MAX_WAYPOINTS 3
+#define QS_RESET_UNIFORMS 16
+
+typedef struct qs_handle qs_handle;
+
+/*
+ * Environment batch configuration.
+ * Replaces: WaypointQuadEnv.__init__ (initial-implementation-v2/rl_env_scaledObs.py:10-38,
+ * initial-implementation-v1/rl_env_scaledObs.py:9-30) x n_envs, as built by
+ * make_vec_env(WaypointQuadEnv, n_envs=8) (initial-implementation-v1/rl_train_vecN.py:10).
+ */
+typedef struct qs_config {
+    int32_t abi_version;       /* QS_ABI_VERSION */
+    int32_t env_version;       /* 1: initial-implementation-v1, 2: initial-implementation-v2 */
+    int32_t obs_scaled;        /* 1: rl_env_scaledObs.py, 0: rl_env.py (raw 17-D obs; v1 only) */
+    int32_t precision;         /* QS_F32 | QS_F64 */
+    int32_t integrator;        /* QS_RK4 | QS_LSODA (LSODA requires QS_F64) */
+    int32_t substeps;          /* RK4 sub-intervals (>= 1) */
+    int32_t action_scale_f32;  /* 1: scale actions in float32 like NumPy>=2 does for float32 actions (default) */
+    int32_t auto_reset;        /* 1: DummyVecEnv semantics, done envs are reset inside the step kernel */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t reserved;
+    int64_t n_envs;            /* envs owned by this handle (this rank's shard) */
+    int64_t env_id_offset;     /* global id of local env 0; Philox is keyed on the global id, so a batch sharded
+                                  over G ranks draws the same episodes as the unsharded batch */
+    uint64_t seed;
+    /* model constants, computed on the host with the same NumPy calls the reference uses
+       (simul_files/model/params.py:10-36) so that invA / invI are bit-identical */
+    double mass, g, dt;
+    double inertia[9], inv_inertia[9];
+    double mix[16], inv_mix[16];
+    double max_prop_thrust, min_prop_thrust; /* maxF/4, minF/4 */
+    double sin_tab[QS_MAX_WAYPOINTS], cos_tab[QS_MAX_WAYPOINTS]; /* sin/cos(2*pi*j/K), j=1..K (utils2/utils.py:41,84-85) */
+    double lsoda_rtol, lsoda_atol;           /* odeint defaults: 1.49012e-8 */
+} qs_config;
+
+/*
+ * Canonical float64 struct-of-arrays view of the hidden env state, for parity injection/extraction.
+ * All pointers are device pointers with n_envs rows; any pointer may be NULL (field skipped).
+ * Replaces: direct attribute access on the reference env (env.quadcopter.state, env.waypoint_list, ...,
+ * as read by initial-implementation-v2/simul_files/quadPlot.py:299-326 and runsim_scaledObs.py:29,65-66).
+ */
+typedef struct qs_state_view {
+    double* y;              /* [n,13] pos, vel, quat(wxyz), omega */
+    double* wp_list;        /* [n,QS_MAX_WAYPOINTS,3] */
+    int32_t* n_wp;          /* [n] */
+    int32_t* wp_index;      /* [n] */
+    double* last_distance;  /* [n], NaN == None */
+    int32_t* current_step;  /* [n] */
+    int32_t* counter;       /* [n] (v2) */
+    uint8_t* final_reached; /* [n] (v2; == counter_activated) */
+    double* final_yaw;      /* [n] (v2) */
+    double* ep_return;      /* [n] Monitor-style running episode return */
+    int32_t* episode;       /* [n] resets so far (Philox counter word) */
+} qs_state_view;
+
+/* Library / lifecycle ---------------------------------------------------------------------------- */
+int qs_abi_version(void);
+const char* qs_last_error(const qs_handle* h);
+int qs_create(const qs_config* cfg, qs_handle** out);
+int qs_destroy(qs_handle* h);
+int qs_obs_dim(const qs_handle* h);               /* 20 (v2) or 17 (v1) */
+int64_t qs_state_bytes_per_env(const qs_handle* h); /* bytes of hidden state per env held in HBM */
+
+/*
+ * Reset.  Replaces WaypointQuadEnv.reset (v2 rl_env_scaledObs.py:40-79, v1 :32-51) / VecEnv.reset().
+ * env_mask: NULL = all envs, else u8[n] (non-zero = reset).  obs_out: f32[n,obs_dim] (only reset rows written).
+ */
+int qs_reset(qs_handle* h, const uint8_t* env_mask, float* obs_out, void* stream);
+
+/*
+ * One env step for the whole batch: physics + reward + termination + observation (+ auto-reset).
+ * Replaces WaypointQuadEnv.step (v2 rl_env_scaledObs.py:123-231, v1 :85-168) over Quadcopter.update
+ * (simul_files/model/quadcopter.py:105-114), looped by DummyVecEnv.step_wait.
+ *   actions          f32[n,4]   (not clipped here: SB3 clips before env.step)
+ *   obs_out          f32[n,obs_dim]  post-step obs, or the reset obs for envs that were auto-reset
+ *   reward_out       f32[n] (QS_F32) or f64[n] (QS_F64)
+ *   flags_out        u8[n]  QS_FLAG_* bits
+ *   terminal_obs_out f32[n,obs_dim] or NULL; written only for done envs (info['terminal_observation'])
+ *   ep_return_out    same dtype as reward_out, or NULL; written only for done envs (Monitor 'r')
+ *   ep_len_out       i32[n] or NULL; written only for done envs (Monitor 'l')
+ */
+int qs_step(qs_handle* h, const float* actions, float* obs_out, void* reward_out, uint8_t* flags_out,
+            float* terminal_obs_out, void* ep_return_out, int32_t* ep_len_out, void* stream);
+
+int qs_get_state(qs_handle* h, const qs_state_view* out, void* stream);
+int qs_set_state(qs_handle* h, const qs_state_view* in, void* stream);
+
+/* The QS_RESET_UNIFORMS unit uniforms the reset of (global env id, episode) consumes: f64[n,16]. Test hook. */
+int qs_reset_uniforms(qs_handle* h, const int64_t* env_ids, const int32_t* episodes, int64_t n, double* out,
+                      void* stream);
+
+/*
+ * LSODA diagnostics of the most recent qs_step in QS_LSODA mode: i32[n,4] = nst, nfe, nqu, status and
+ * f64[n,2] = hu, tcur -- the counters scipy's odeint(full_output=True) reports.  Either may be NULL.
+ */
+int qs_lsoda_stats(qs_handle* h, int32_t* counters_out, double* steps_out, void* stream);
+
+/* VecNormalize --------------------------------------------------------------------------------------
+ * Replaces stable_baselines3 VecNormalize(norm_obs=True) / RunningMeanStd.update
+ * (call sites initial-implementation-v1/rl_train_vecN.py:11, rl_checkpoint_train_vecN.py:23-28).
+ * stats layout (device, f64): [0]=count, [1..d]=mean, [1+d..2d]=var.
+ */
+/* batch moments of x f32[n,d] -> moments f64[1+2d] = (n, mean[d], M2[d]) ; scratch: f64[qs_moments_scratch_len(d)] */
+int64_t qs_moments_scratch_len(int d);
+int qs_batch_moments(const float* x, int64_t n, int d, double* moments_out, double* scratch, void* stream);
+/* merge `k` moment triplets f64[k,1+2d] (e.g. all-gathered over ranks) into the running stats (Chan et al.) */
+int qs_vecnorm_merge(double* stats, const double* moments, int k, int d, void* stream);
+/* out = clip((x - mean) / sqrt(var + eps), +-clip) as f32; out may alias x */
+int qs_vecnorm_apply(const float* x, float* out, int64_t n, int d, const double* stats, double eps, double clip,
+                     void* stream);
+
+/* MlpPolicy rollout forward -----------------------------------------------------------------------
+ * Replaces stable_baselines3 ActorCriticPolicy.forward for MlpPolicy(net_arch=[128,64,64], Tanh)
+ * (PPO("MlpPolicy", ...) at initial-implementation-v2/rl_train.py:27-53, v1/rl_train_vecN.py:13-33).
+ * params: one f32 device blob, layout given by qs_policy_param_offsets() (actor trunk, critic trunk, heads, log_std).
+ *   obs      f32[n,d]
+ *   noise    f32[n,4] standard normal, or NULL for deterministic actions (mean)
+ *   actions  f32[n,4]  (unclipped, what SB3 stores)     values f32[n]     logp f32[n]
+ */
+int64_t qs_policy_param_count(int obs_dim);
+int qs_policy_forward(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
+                      float* actions, float* values, float* logp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADSIM_H */

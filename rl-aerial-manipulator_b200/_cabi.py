@@ -1,0 +1,127 @@
+"""ctypes binding of libquadsim.so (include/quadsim.h).  Torch tensors are the only buffers: every
+pointer handed to the library is `tensor.data_ptr()` of a CUDA tensor, every stream a raw cudaStream_t.
+
+There is no CPU fallback: if the shared library is missing (not built) or no B200 is visible, loading /
+`qs_create` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import params
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libquadsim.so")
+
+QS_ABI_VERSION = 1
+QS_F32, QS_F64 = 0, 1
+QS_RK4, QS_LSODA = 0, 1
+FLAG_TERMINATED, FLAG_TRUNCATED, FLAG_SUCCESS, FLAG_STOPPED = 0x01, 0x02, 0x04, 0x08
+FLAG_CRASHED, FLAG_OOB, FLAG_LSODA_FAIL = 0x10, 0x20, 0x80
+MAX_WAYPOINTS = 3
+RESET_UNIFORMS = 16
+
+
+class QsConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("env_version", C.c_int32), ("obs_scaled", C.c_int32), ("precision", C.c_int32),
+        ("integrator", C.c_int32), ("substeps", C.c_int32), ("action_scale_f32", C.c_int32), ("auto_reset", C.c_int32),
+        ("device", C.c_int32), ("reserved", C.c_int32),
+        ("n_envs", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
+        ("mass", C.c_double), ("g", C.c_double), ("dt", C.c_double),
+        ("inertia", C.c_double * 9), ("inv_inertia", C.c_double * 9),
+        ("mix", C.c_double * 16), ("inv_mix", C.c_double * 16),
+        ("max_prop_thrust", C.c_double), ("min_prop_thrust", C.c_double),
+        ("sin_tab", C.c_double * 3), ("cos_tab", C.c_double * 3),
+        ("lsoda_rtol", C.c_double), ("lsoda_atol", C.c_double),
+    ]
+
+
+class QsStateView(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in (
+        "y", "wp_list", "n_wp", "wp_index", "last_distance", "current_step", "counter", "final_reached",
+        "final_yaw", "ep_return", "episode")]
+
+
+def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", substeps=1, obs_scaled=True,
+                action_scale_f32=True, auto_reset=True, device=0, env_id_offset=0, seed=0) -> QsConfig:
+    """qs_config with the reference's model constants (params.py) and NumPy-evaluated trig tables."""
+    c = QsConfig()
+    c.abi_version = QS_ABI_VERSION
+    c.env_version = int(env_version)
+    c.obs_scaled = int(bool(obs_scaled))
+    c.precision = {"f32": QS_F32, "f64": QS_F64}[precision]
+    c.integrator = {"rk4": QS_RK4, "lsoda": QS_LSODA}[integrator]
+    c.substeps = int(substeps)
+    c.action_scale_f32 = int(bool(action_scale_f32))
+    c.auto_reset = int(bool(auto_reset))
+    c.device = int(device)
+    c.n_envs = int(n_envs)
+    c.env_id_offset = int(env_id_offset)
+    c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    c.mass, c.g, c.dt = params.mass, params.g, params.dt
+    c.inertia[:] = params.I.reshape(-1).tolist()
+    c.inv_inertia[:] = params.invI.reshape(-1).tolist()
+    c.mix[:] = params.A.reshape(-1).tolist()
+    c.inv_mix[:] = params.invA.reshape(-1).tolist()
+    c.max_prop_thrust = params.maxF / 4
+    c.min_prop_thrust = params.minF / 4
+    k = 1  # waypoints per v2 trajectory (rl_env_scaledObs.py:47); the tables hold sin/cos(2*pi*j/k)
+    for j in range(1, 4):
+        t = min(j, k) / k
+        c.sin_tab[j - 1] = float(np.sin(2 * t * np.pi))
+        c.cos_tab[j - 1] = float(np.cos(2 * np.pi * 1 * t))
+    c.lsoda_rtol = c.lsoda_atol = params.ODEINT_TOL
+    return c
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen libquadsim.so and declare every prototype of include/quadsim.h.  No fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+    lib = C.CDLL(p)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.qs_abi_version.restype = C.c_int
+    lib.qs_last_error.restype = C.c_char_p
+    lib.qs_last_error.argtypes = [vp]
+    lib.qs_create.argtypes = [C.POINTER(QsConfig), C.POINTER(vp)]
+    lib.qs_destroy.argtypes = [vp]
+    lib.qs_obs_dim.argtypes = [vp]
+    lib.qs_state_bytes_per_env.argtypes = [vp]
+    lib.qs_state_bytes_per_env.restype = i64
+    lib.qs_reset.argtypes = [vp, vp, vp, vp]
+    lib.qs_step.argtypes = [vp] + [vp] * 7 + [vp]
+    lib.qs_get_state.argtypes = [vp, C.POINTER(QsStateView), vp]
+    lib.qs_set_state.argtypes = [vp, C.POINTER(QsStateView), vp]
+    lib.qs_reset_uniforms.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.qs_lsoda_stats.argtypes = [vp, vp, vp, vp]
+    for name in ("qs_create", "qs_destroy", "qs_obs_dim", "qs_reset", "qs_step", "qs_get_state", "qs_set_state",
+                 "qs_reset_uniforms", "qs_lsoda_stats"):
+        getattr(lib, name).restype = C.c_int
+    if lib.qs_abi_version() != QS_ABI_VERSION:
+        raise RuntimeError(f"libquadsim ABI {lib.qs_abi_version()} != binding ABI {QS_ABI_VERSION}; rebuild")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class QuadsimError(RuntimeError):
+    pass
+
+
+def check(lib, handle, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.qs_last_error(handle)
+        raise QuadsimError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")

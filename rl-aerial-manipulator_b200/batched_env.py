@@ -1,0 +1,167 @@
+"""BatchedQuadEnv -- native tensor API over libquadsim (one handle = one shard of envs on one B200).
+
+This is the throughput surface: every input and output is a torch CUDA tensor, nothing is copied to the
+host, and calls are ordered on the current torch CUDA stream.  The SB3-compatible NumPy surface
+(`reset / step_async / step_wait`, `infos` dicts) is `vec_env.QuadVecEnv`, built on top of this class.
+
+Replaces, for N envs at once (reference root-relative paths):
+    WaypointQuadEnv.reset / step   initial-implementation-v2/rl_env_scaledObs.py:40-231
+                                   initial-implementation-v1/rl_env_scaledObs.py:32-168, rl_env.py
+    Quadcopter.update              simul_files/model/quadcopter.py:105-114
+    DummyVecEnv auto-reset         (stable_baselines3, call site initial-implementation-v1/rl_train_vecN.py:10)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _cabi
+from ._cabi import QsStateView, check, load_library, make_config
+
+OBS_DIM = {1: 17, 2: 20}
+
+_STATE_FIELDS = {
+    "y": (torch.float64, (13,)), "wp_list": (torch.float64, (3, 3)), "n_wp": (torch.int32, ()),
+    "wp_index": (torch.int32, ()), "last_distance": (torch.float64, ()), "current_step": (torch.int32, ()),
+    "counter": (torch.int32, ()), "final_reached": (torch.uint8, ()), "final_yaw": (torch.float64, ()),
+    "ep_return": (torch.float64, ()), "episode": (torch.int32, ()),
+}
+
+
+@dataclass
+class StepOut:
+    obs: torch.Tensor            # f32[n, obs_dim]; reset obs for envs that finished (auto_reset)
+    reward: torch.Tensor         # f32[n] or f64[n]
+    flags: torch.Tensor          # u8[n], QS_FLAG_* bits
+    terminal_obs: torch.Tensor   # f32[n, obs_dim]; rows valid where done
+    ep_return: torch.Tensor      # rows valid where done
+    ep_len: torch.Tensor         # i32[n]; rows valid where done
+
+    @property
+    def done(self) -> torch.Tensor:
+        return (self.flags & 3) != 0
+
+    @property
+    def terminated(self) -> torch.Tensor:
+        return (self.flags & _cabi.FLAG_TERMINATED) != 0
+
+    @property
+    def truncated(self) -> torch.Tensor:
+        return (self.flags & _cabi.FLAG_TRUNCATED) != 0
+
+
+class BatchedQuadEnv:
+    """N independent WaypointQuadEnv instances stepped by one fused sm_100a kernel."""
+
+    def __init__(self, n_envs: int, env_version: int = 2, precision: str = "f32", integrator: str = "rk4",
+                 substeps: int = 1, obs_scaled: bool = True, action_scale_f32: bool = True, auto_reset: bool = True,
+                 device: int | torch.device | None = None, env_id_offset: int = 0, seed: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedQuadEnv needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+        self.lib = load_library()
+        self.cfg = make_config(env_version=env_version, n_envs=n_envs, precision=precision, integrator=integrator,
+                               substeps=substeps, obs_scaled=obs_scaled, action_scale_f32=action_scale_f32,
+                               auto_reset=auto_reset, device=self.device.index, env_id_offset=env_id_offset, seed=seed)
+        self.n_envs = int(n_envs)
+        self.env_version = int(env_version)
+        self.obs_dim = OBS_DIM[self.env_version]
+        self.precision = precision
+        self.integrator = integrator
+        self.real_dtype = torch.float32 if precision == "f32" else torch.float64
+        self._h = C.c_void_p()
+        check(self.lib, None, self.lib.qs_create(C.byref(self.cfg), C.byref(self._h)), "qs_create")
+        n, d = self.n_envs, self.obs_dim
+        dev = self.device
+        # persistent output buffers (caller-owned from the library's point of view)
+        self.obs = torch.empty((n, d), dtype=torch.float32, device=dev)
+        self.reward = torch.empty((n,), dtype=self.real_dtype, device=dev)
+        self.flags = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        self.terminal_obs = torch.zeros((n, d), dtype=torch.float32, device=dev)
+        self.ep_return = torch.zeros((n,), dtype=self.real_dtype, device=dev)
+        self.ep_len = torch.zeros((n,), dtype=torch.int32, device=dev)
+
+    # -- lifecycle ---------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.qs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def state_bytes_per_env(self) -> int:
+        return int(self.lib.qs_state_bytes_per_env(self._h))
+
+    # -- env API -----------------------------------------------------------------------------------
+    def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        """Reset all envs (mask None) or the masked ones; returns the obs buffer f32[n, obs_dim]."""
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mp = C.c_void_p(mask.data_ptr())
+        check(self.lib, self._h, self.lib.qs_reset(self._h, mp, C.c_void_p(self.obs.data_ptr()), self._stream()), "qs_reset")
+        return self.obs
+
+    def step(self, actions: torch.Tensor) -> StepOut:
+        """actions f32[n,4] on this device (not clipped here: SB3 clips before env.step)."""
+        if actions.dtype != torch.float32 or actions.device != self.device or tuple(actions.shape) != (self.n_envs, 4):
+            raise ValueError(f"actions must be float32[{self.n_envs},4] on {self.device}")
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        check(self.lib, self._h,
+              self.lib.qs_step(self._h, p(actions), p(self.obs), p(self.reward), p(self.flags), p(self.terminal_obs),
+                               p(self.ep_return), p(self.ep_len), self._stream()), "qs_step")
+        return StepOut(self.obs, self.reward, self.flags, self.terminal_obs, self.ep_return, self.ep_len)
+
+    # -- state injection / extraction (parity tests, plotting façade) ------------------------------
+    def get_state(self, fields=None) -> dict[str, torch.Tensor]:
+        fields = list(fields or _STATE_FIELDS)
+        out, view = {}, QsStateView()
+        for name in fields:
+            dt, shp = _STATE_FIELDS[name]
+            out[name] = torch.empty((self.n_envs, *shp), dtype=dt, device=self.device)
+            setattr(view, name, out[name].data_ptr())
+        check(self.lib, self._h, self.lib.qs_get_state(self._h, C.byref(view), self._stream()), "qs_get_state")
+        return out
+
+    def set_state(self, **fields) -> None:
+        view, keep = QsStateView(), []
+        for name, val in fields.items():
+            dt, shp = _STATE_FIELDS[name]
+            t = torch.as_tensor(val).to(device=self.device, dtype=dt).contiguous()
+            if tuple(t.shape) != (self.n_envs, *shp):
+                raise ValueError(f"{name}: expected shape {(self.n_envs, *shp)}, got {tuple(t.shape)}")
+            keep.append(t)
+            setattr(view, name, t.data_ptr())
+        check(self.lib, self._h, self.lib.qs_set_state(self._h, C.byref(view), self._stream()), "qs_set_state")
+        torch.cuda.current_stream(self.device).synchronize()  # `keep` must outlive the kernel
+
+    def reset_uniforms(self, env_ids: torch.Tensor, episodes: torch.Tensor) -> torch.Tensor:
+        """The 16 unit uniforms the reset of (global env id, episode) consumes -- test hook."""
+        env_ids = env_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        episodes = episodes.to(device=self.device, dtype=torch.int32).contiguous()
+        out = torch.empty((env_ids.numel(), 16), dtype=torch.float64, device=self.device)
+        check(self.lib, self._h, self.lib.qs_reset_uniforms(self._h, C.c_void_p(env_ids.data_ptr()), C.c_void_p(episodes.data_ptr()),
+                                                           env_ids.numel(), C.c_void_p(out.data_ptr()), self._stream()), "qs_reset_uniforms")
+        return out
+
+    def lsoda_stats(self):
+        """(i32[n,4] = nst, nfe, nqu, status ; f64[n,2] = hu, tcur) of the last step in LSODA mode."""
+        cnt = torch.empty((self.n_envs, 4), dtype=torch.int32, device=self.device)
+        stp = torch.empty((self.n_envs, 2), dtype=torch.float64, device=self.device)
+        check(self.lib, self._h, self.lib.qs_lsoda_stats(self._h, C.c_void_p(cnt.data_ptr()), C.c_void_p(stp.data_ptr()), self._stream()),
+              "qs_lsoda_stats")
+        return cnt, stp

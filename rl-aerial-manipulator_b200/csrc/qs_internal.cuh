@@ -1,0 +1,74 @@
+// qs_internal.cuh -- handle definition and launcher prototypes shared by the translation units of libquadsim.
+#pragma once
+#include "../../include/quadsim.h"
+#include "qs_step_kernel.cuh"
+#include <cuda_runtime.h>
+
+struct qs_handle {
+    qs_config cfg;
+    void* pool;
+    size_t pool_bytes;
+    int64_t bytes_per_env;
+    qs::LsodaTables* ls_tables;
+    int32_t* ls_counters;
+    double* ls_steps;
+    int num_sms;
+    bool initialized;
+    char error[512];
+};
+
+namespace qs {
+void set_error(qs_handle* h, const char* fmt, ...);
+
+int launch_step_f32(qs_handle* h, const float* actions, float* obs, float* reward, uint8_t* flags, float* term_obs,
+                    float* ep_ret, int32_t* ep_len, cudaStream_t st);
+int launch_step_f64(qs_handle* h, const float* actions, float* obs, double* reward, uint8_t* flags, float* term_obs,
+                    double* ep_ret, int32_t* ep_len, cudaStream_t st);
+int launch_step_lsoda(qs_handle* h, const float* actions, float* obs, double* reward, uint8_t* flags, float* term_obs,
+                      double* ep_ret, int32_t* ep_len, cudaStream_t st);
+
+// Fill StepParams from the handle (everything except the per-call buffers).
+template <typename Real>
+inline StepParams<Real> base_params(const qs_handle* h) {
+    const qs_config& c = h->cfg;
+    StepParams<Real> p;
+    p.pool = h->pool;
+    p.n = c.n_envs;
+    p.ls_tables = h->ls_tables;
+    p.ls_counters = h->ls_counters;
+    p.ls_steps = h->ls_steps;
+    p.substeps = c.substeps;
+    p.obs_scaled = c.obs_scaled;
+    p.scale_f32 = c.action_scale_f32;
+    p.auto_reset = c.auto_reset;
+    p.seed = c.seed;
+    p.env_id_offset = c.env_id_offset;
+    p.rtol = c.lsoda_rtol;
+    p.atol = c.lsoda_atol;
+    Model<Real>& m = p.model;
+    m.mass = (Real)c.mass;
+    m.inv_mass = (Real)(1.0 / c.mass);
+    m.g = (Real)c.g;
+    m.dt = (Real)c.dt;
+    m.I00 = (Real)c.inertia[0]; m.I02 = (Real)c.inertia[2]; m.I11 = (Real)c.inertia[4];
+    m.I20 = (Real)c.inertia[6]; m.I22 = (Real)c.inertia[8];
+    m.J00 = (Real)c.inv_inertia[0]; m.J02 = (Real)c.inv_inertia[2]; m.J11 = (Real)c.inv_inertia[4];
+    m.J20 = (Real)c.inv_inertia[6]; m.J22 = (Real)c.inv_inertia[8];
+    for (int i = 0; i < 16; ++i) { m.mix[i] = (Real)c.mix[i]; m.inv_mix[i] = (Real)c.inv_mix[i]; }
+    m.tmax = (Real)c.max_prop_thrust;
+    m.tmin = (Real)c.min_prop_thrust;
+    for (int i = 0; i < 3; ++i) { p.rc.sin_tab[i] = c.sin_tab[i]; p.rc.cos_tab[i] = c.cos_tab[i]; }
+    return p;
+}
+
+// Persistent grid: enough CTAs to fill every SM at the kernel's occupancy, never more than the work needs.
+template <typename Kernel>
+inline unsigned step_grid(const qs_handle* h, Kernel k, int block) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, 0);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = (h->cfg.n_envs + block - 1) / block;
+    const int64_t cap = (int64_t)per_sm * h->num_sms;
+    return (unsigned)(need < cap ? need : cap);
+}
+}  // namespace qs

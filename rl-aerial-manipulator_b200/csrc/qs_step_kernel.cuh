@@ -1,0 +1,164 @@
+// qs_step_kernel.cuh -- the fused env-step kernel: one thread per env, hidden state in registers.
+//
+//   load state (LDG.128 planes) + action (LDG.128)
+//   -> action scaling, mixer, per-prop clamp            [quadcopter.py:105-112]
+//   -> integrator: RK4 x substeps, or the LSODA port     [quadcopter.py:113]
+//   -> quaternion renormalisation                        [quadcopter.py:114]
+//   -> reward + waypoint/hold/termination state machine  [rl_env_scaledObs.py step/_calculate_reward]
+//   -> observation (scaled, float32)                     [_get_observation]
+//   -> auto-reset with Philox draws for done envs        [DummyVecEnv.step_wait + reset()]
+//   -> store state planes; obs rows leave through a per-warp shared-memory transpose so the
+//      [n, obs_dim] row-major output is written with full 128-bit coalesced stores.
+#pragma once
+#include "qs_pool.cuh"
+#include "qs_lsoda.cuh"
+
+namespace qs {
+
+enum : int { INTEG_RK4 = 0, INTEG_LSODA = 1 };
+
+template <typename Real>
+struct StepParams {
+    void* pool;
+    int64_t n;
+    const float* actions;       // [n,4]
+    float* obs_out;             // [n,OBS]
+    Real* reward_out;           // [n]
+    uint8_t* flags_out;         // [n]
+    float* term_obs_out;        // [n,OBS] or null
+    Real* ep_ret_out;           // [n] or null
+    int32_t* ep_len_out;        // [n] or null
+    const LsodaTables* ls_tables; // device copy of the method coefficients (LSODA mode)
+    int32_t* ls_counters;       // [n,4] or null (LSODA diagnostics)
+    double* ls_steps;           // [n,2] or null
+    int substeps, obs_scaled, scale_f32, auto_reset;
+    uint64_t seed;
+    int64_t env_id_offset;
+    double rtol, atol;
+    Model<Real> model;
+    ResetConsts rc;
+};
+
+#if defined(__CUDACC__)
+constexpr int STEP_BLOCK = 128;
+
+// Row-major [32, OBS] tile of one warp -> global, 128 bits per lane per store.
+template <int OBS>
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, const float* tile /*[32][OBS+1]*/, int lane, int valid_rows) {
+    constexpr int TOTAL = 32 * OBS;
+    const int valid = valid_rows * OBS;
+#pragma unroll
+    for (int base = 0; base < TOTAL; base += 128) {
+        const int e = base + 4 * lane;
+        if (e + 3 < valid) {
+            float4 v;
+            v.x = tile[((e + 0) / OBS) * (OBS + 1) + (e + 0) % OBS];
+            v.y = tile[((e + 1) / OBS) * (OBS + 1) + (e + 1) % OBS];
+            v.z = tile[((e + 2) / OBS) * (OBS + 1) + (e + 2) % OBS];
+            v.w = tile[((e + 3) / OBS) * (OBS + 1) + (e + 3) % OBS];
+            __stcs(reinterpret_cast<float4*>(dst + e), v);
+        } else {
+            for (int j = 0; j < 4; ++j)
+                if (e + j < valid) dst[e + j] = tile[((e + j) / OBS) * (OBS + 1) + (e + j) % OBS];
+        }
+    }
+}
+
+template <typename Real, int VER, int INTEG>
+__global__ void __launch_bounds__(STEP_BLOCK) env_step_kernel(const StepParams<Real> p) {
+    constexpr int OBS = EnvTraits<VER>::OBS;
+    __shared__ float s_tile[STEP_BLOCK / 32][32 * (OBS + 1)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * (STEP_BLOCK / 32);
+    const int64_t n_warp_tiles = (p.n + 31) / 32;
+    float* tile = s_tile[warp];
+
+    for (int64_t wt = (int64_t)blockIdx.x * (STEP_BLOCK / 32) + warp; wt < n_warp_tiles; wt += warps_total) {
+        const int64_t e0 = wt * 32;
+        const int64_t e = e0 + lane;
+        const bool live = e < p.n;
+        float obs[OBS];
+        if (live) {
+            EnvState<Real, VER> s;
+            pool_load<Real, VER>(p.pool, p.n, e, s);
+            const float4 a4 = __ldcs(reinterpret_cast<const float4*>(p.actions) + e);
+            const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+
+            Real Fcmd, Mcmd[3], F, M[3];
+            scale_action<Real>(p.model, act, p.scale_f32, Fcmd, Mcmd);
+            mix_and_clamp<Real>(p.model, Fcmd, Mcmd, F, M);
+            uint32_t flags = 0;
+            if constexpr (INTEG == INTEG_LSODA) {
+                LsodaResult r;
+                lsoda_advance(p.model, *p.ls_tables, s.y, F, M, p.model.dt, p.rtol, p.atol, r);
+                if (r.status & ~LS_WOULD_SWITCH) flags |= FLAG_LSODA_FAIL;
+                if (p.ls_counters) {
+                    reinterpret_cast<int4*>(p.ls_counters)[e] = make_int4(r.nst, r.nfe, r.nqu, r.status);
+                    reinterpret_cast<double2*>(p.ls_steps)[e] = make_double2(r.hu, r.tcur);
+                }
+            } else {
+                rk4_step<Real>(p.model, s.y, F, M, p.substeps);
+            }
+            renormalise_quat<Real>(s.y);
+
+            Real reward;
+            int ep_len;
+            flags |= step_logic<Real, VER>(s, reward, ep_len);
+            s.ep_ret += reward;
+            make_obs<Real, VER>(s, p.obs_scaled, obs);
+
+            p.reward_out[e] = reward;
+            p.flags_out[e] = (uint8_t)flags;
+            if (flags & (FLAG_TERMINATED | FLAG_TRUNCATED)) {
+                if (p.term_obs_out) {
+                    float* row = p.term_obs_out + e * OBS;
+#pragma unroll
+                    for (int i = 0; i < OBS; ++i) row[i] = obs[i];
+                }
+                if (p.ep_ret_out) p.ep_ret_out[e] = s.ep_ret;
+                if (p.ep_len_out) p.ep_len_out[e] = ep_len;
+                if (p.auto_reset) {
+                    s.episode += 1;
+                    reset_env<Real, VER>(s, p.rc, p.seed, (uint64_t)(p.env_id_offset + e));
+                    make_obs<Real, VER>(s, p.obs_scaled, obs);
+                }
+            }
+            pool_store<Real, VER>(p.pool, p.n, e, s);
+#pragma unroll
+            for (int i = 0; i < OBS; ++i) tile[lane * (OBS + 1) + i] = obs[i];
+        }
+        __syncwarp();
+        const int64_t rem = p.n - e0;
+        warp_store_rows<OBS>(p.obs_out + e0 * OBS, tile, lane, rem < 32 ? (int)rem : 32);
+        __syncwarp();
+    }
+}
+
+// Reset (all envs or a mask) and write their observation.
+template <typename Real, int VER>
+__global__ void __launch_bounds__(256) env_reset_kernel(void* pool, int64_t n, const uint8_t* mask, float* obs_out,
+                                                         int obs_scaled, uint64_t seed, int64_t env_id_offset,
+                                                         ResetConsts rc, int first) {
+    constexpr int OBS = EnvTraits<VER>::OBS;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mask && !mask[e]) return;
+    EnvState<Real, VER> s;
+    if (first) {
+        s.episode = 0;
+    } else {
+        pool_load<Real, VER>(pool, n, e, s);
+        s.episode += 1;
+    }
+    reset_env<Real, VER>(s, rc, seed, (uint64_t)(env_id_offset + e));
+    pool_store<Real, VER>(pool, n, e, s);
+    if (obs_out) {
+        float obs[OBS];
+        make_obs<Real, VER>(s, obs_scaled, obs);
+#pragma unroll
+        for (int i = 0; i < OBS; ++i) obs_out[e * OBS + i] = obs[i];
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace qs

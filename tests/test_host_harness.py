@@ -1,0 +1,193 @@
+"""The product's device code (csrc/*.cuh), compiled for the host with g++, against the golden vectors of the
+unmodified reference and against the oracle.  Runs on the CPU-only build box; the same checks run on the
+B200 through the C-ABI in tests/test_gpu_parity.py.
+
+Tolerances (north_star): float64 single step 1e-9 relative; float32 1e-4; flags bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import rl_aerial_manipulator_b200 as qsim
+from oracle import quad_oracle as qo
+from harness_util import HostHarness, golden_state, flags_from_golden
+
+VERS = {"v2": 2, "v1": 1, "v1_raw": 1}
+
+
+@pytest.fixture(scope="module")
+def hh():
+    return HostHarness(qsim.make_config(env_version=2, precision="f64", integrator="lsoda", seed=1234))
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_philox_known_answers(hh):
+    """Random123 known-answer vectors for philox4x32-10."""
+    np.testing.assert_array_equal(hh.philox([0, 0, 0, 0], [0, 0]), [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8])
+    np.testing.assert_array_equal(hh.philox([0xffffffff] * 4, [0xffffffff] * 2), [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd])
+    np.testing.assert_array_equal(hh.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]),
+                                  [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])
+
+
+def test_uniforms_are_uniform(hh):
+    u = np.array([hh.uniforms(7, e, ep) for e in range(400) for ep in range(3)])
+    assert u.min() >= 0.0 and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
+    assert len(np.unique(u)) == u.size  # distinct (env, episode) -> distinct draws
+    # different seed / env / episode all change the block
+    assert not np.array_equal(hh.uniforms(7, 1, 0), hh.uniforms(8, 1, 0))
+    assert not np.array_equal(hh.uniforms(7, 1, 0), hh.uniforms(7, 1, 1))
+    assert not np.array_equal(hh.uniforms(7, 1, 0), hh.uniforms(7, 2**32 + 1, 0))
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1"])
+def test_lsoda_port_matches_scipy_counters(hh, golden_dir, variant):
+    """nst / nfe / nqu / hu / tcur and the raw result of the reference's own odeint calls."""
+    g = load(golden_dir, f"step_{variant}.npz")
+    n = len(g["reward"])
+    exact = 0
+    hu_close = 0
+    worst = 0.0
+    for i in range(n):
+        F, M = hh.mix(g["action"][i])
+        assert abs(F - g["lsoda_F_clamped"][i]) <= 1e-15 * max(1.0, abs(F))  # BLAS gemv (FMA) vs plain products: <= 2 ulp
+        np.testing.assert_allclose(M, g["lsoda_M_clamped"][i], rtol=1e-13, atol=1e-17)  # yaw moment cancels to ~1e-4 of its terms
+        y, st = hh.lsoda(g["pre_y"][i], F, M)
+        assert st["status"] == 0
+        same = (st["nst"], st["nfe"], st["nqu"]) == (g["lsoda_nst"][i], g["lsoda_nfe"][i], g["lsoda_nqu"][i])
+        exact += same
+        if same:
+            hu_close += abs(st["hu"] - g["lsoda_hu"][i]) < 1e-4 * g["lsoda_hu"][i]
+        err = np.abs(y - g["lsoda_y_raw"][i]) / np.maximum(np.abs(g["lsoda_y_raw"][i]), 1.0)
+        worst = max(worst, err.max())
+    assert exact >= 0.98 * n, f"only {exact}/{n} calls reproduce scipy's step sequence"
+    # measured here: 491/491 calls reproduce scipy's (nst, nfe, nqu); last step size within 7e-5 relative;
+    # worst state error 4.8e-12.  (With the closed-form rotation instead of the reference's arccos route the
+    # near-hover calls pick visibly different steps and the error grows to 1.6e-9 -- see qs_model.cuh.)
+    assert hu_close >= 0.99 * n
+    assert worst < 1e-10, worst
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1", "v1_raw"])
+def test_f64_lsoda_step_vs_reference_golden(hh, golden_dir, variant):
+    g = load(golden_dir, f"step_{variant}.npz")
+    ver = VERS[variant]
+    checked = 0
+    for i in range(len(g["reward"])):
+        if ver == 2 and g["pre_n_wp"][i] > 1:
+            continue  # multi-waypoint v2 lists are the reference's commented-out alternative; kernel holds 1
+        st, obs, rew, flags, ep_len, ls = hh.step(ver, golden_state(g, "pre_", i), g["action"][i], f32=False, integ="lsoda",
+                                                 obs_scaled=(variant != "v1_raw"))
+        case = g["case"][i]
+        np.testing.assert_allclose(st["y"], g["post_y"][i], rtol=1e-9, atol=1e-10, err_msg=f"{i} {case}")
+        assert st["wp_index"] == g["post_wp_index"][i] and st["current_step"] == g["post_current_step"][i], (i, case)
+        if ver == 2:
+            assert st["counter"] == g["post_counter"][i] and st["final_reached"] == g["post_final_reached"][i], (i, case)
+        if case != "on_waypoint_nan":
+            assert flags == flags_from_golden(g, i), (i, case, flags)
+            np.testing.assert_allclose(rew, g["reward"][i], rtol=1e-9, atol=1e-9, err_msg=f"{i} {case}")
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=3e-7, atol=1e-9, err_msg=f"{i} {case}")
+        np.testing.assert_allclose(st["last_distance"], g["post_last_distance"][i], rtol=1e-9, atol=1e-10)
+        checked += 1
+    assert checked > 200
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1"])
+def test_step_logic_exact_on_reference_state(hh, golden_dir, variant):
+    """Feed the golden post-update dynamics state through a zero-length physics step: logic must be exact."""
+    # RK4 with dt -> the harness always integrates, so this test drives the logic through the oracle instead:
+    g = load(golden_dir, f"step_{variant}.npz")
+    ver = VERS[variant]
+    b = qo.EnvBatch.empty(variant, len(g["reward"]), max_wp=3)
+    for f in ("y", "wp_list", "n_wp", "wp_index", "cur_wp", "last_distance", "current_step", "counter", "final_reached", "final_yaw"):
+        setattr(b, f, np.array(g["pre_" + f]))
+    with np.errstate(all="ignore"):
+        obs_o, rew_o, term_o, trunc_o, info_o = qo.step(b, g["action"], integrator="rk4", substeps=4)
+    for i in range(len(g["reward"])):
+        if ver == 2 and g["pre_n_wp"][i] > 1:
+            continue
+        st, obs, rew, flags, ep_len, _ = hh.step(ver, golden_state(g, "pre_", i), g["action"][i], f32=False, integ="rk4", substeps=4)
+        np.testing.assert_allclose(st["y"], b.y[i], rtol=1e-12, atol=1e-13)
+        if g["case"][i] == "on_waypoint_nan":
+            continue
+        want = int(term_o[i]) | int(trunc_o[i]) << 1 | (int(info_o[i]) & 0xF) << 2
+        assert flags == want, (i, g["case"][i])
+        np.testing.assert_allclose(rew, rew_o[i], rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(obs, obs_o[i], rtol=2e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1"])
+def test_f32_rk4_step_within_1e4(hh, golden_dir, variant):
+    """float32 throughput mode vs the float64 reference: 1e-4 relative (north_star), flags equal away from thresholds."""
+    g = load(golden_dir, f"step_{variant}.npz")
+    ver = VERS[variant]
+    n_flag = 0
+    for i in range(len(g["reward"])):
+        if ver == 2 and g["pre_n_wp"][i] > 1:
+            continue
+        case = g["case"][i]
+        if case == "on_waypoint_nan":
+            continue
+        st, obs, rew, flags, ep_len, _ = hh.step(ver, golden_state(g, "pre_", i), g["action"][i], f32=True, integ="rk4", substeps=1)
+        np.testing.assert_allclose(st["y"], g["post_y"][i], rtol=1e-4, atol=1e-5, err_msg=f"{i} {case}")
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=1e-4, atol=1e-5, err_msg=f"{i} {case}")
+        assert flags == flags_from_golden(g, i), (i, case)
+        n_flag += 1
+        # the +2 progress bonus flips when |delta distance| is below float32 resolution; skip those few
+        ld, d = g["pre_last_distance"][i], g["post_last_distance"][i]
+        if not np.isnan(ld) and abs(ld - d) < 2e-6:
+            continue
+        np.testing.assert_allclose(rew, g["reward"][i], rtol=1e-4, atol=2e-4, err_msg=f"{i} {case}")
+    assert n_flag > 200
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1"])
+def test_reset_matches_oracle_on_same_uniforms(hh, variant):
+    ver = VERS[variant]
+    n = 300
+    b = qo.EnvBatch.empty(variant, n, max_wp=3)
+    U = np.array([hh.uniforms(1234, 10_000_000_000 + e, e % 5) for e in range(n)])
+    qo.reset_from_uniforms(b, np.arange(n), U)
+    obs_o = qo.observe(b)
+    kinds = set()
+    for e in range(n):
+        st, obs = hh.reset(ver, 10_000_000_000 + e, e % 5)
+        np.testing.assert_array_equal(st["y"], b.y[e])
+        assert st["n_wp"] == b.n_wp[e] and st["wp_index"] == 0 and st["current_step"] == 0 and not st["has_last"]
+        k = 1 if ver == 2 else 2
+        np.testing.assert_array_equal(st["wp_list"][:k], b.wp_list[e][:k])
+        if ver == 2:
+            assert st["final_yaw"] == b.final_yaw[e]
+        np.testing.assert_array_equal(obs, obs_o[e])
+        kinds.add(int(b.n_wp[e]) if ver == 1 else (0 if U[e, 8] < 0.3 else 1 if U[e, 9] < 0.6 else 2))
+    assert len(kinds) == (3 if ver == 2 else 2)
+
+
+def test_reset_known_answers_from_reference(hh, golden_dir):
+    """Golden reset vectors were produced by the reference on scripted uniforms; replay them through the
+    oracle (already pinned) is covered elsewhere -- here: the kernel's draw order equals the oracle's for the
+    reference's uniform blocks by checking trajectory-kind statistics of the device generator."""
+    n = 6000
+    kinds = np.zeros(3)
+    for e in range(n):
+        u = hh.uniforms(99, e, 0)
+        kinds[0 if u[8] < 0.3 else 1 if u[9] < 0.6 else 2] += 1
+    np.testing.assert_allclose(kinds / n, [0.30, 0.42, 0.28], atol=0.02)  # mixture weights of rl_env_scaledObs.py:63-68
+
+
+def test_euler_matches_oracle(hh):
+    rng = np.random.default_rng(3)
+    q = rng.normal(size=(500, 4))
+    q[0] = [np.sqrt(0.5), 0, np.sqrt(0.5), 0]
+    q[1] = [np.sqrt(0.5), 0, -np.sqrt(0.5), 0]
+    out = np.zeros((500, 3))
+    import ctypes as C
+    for i in range(500):
+        qi = np.ascontiguousarray(q[i])
+        hh.lib.hh_rpy(qi.ctypes.data_as(C.c_void_p), out[i].ctypes.data_as(C.c_void_p))
+    r, p, y = qo.quat_to_rpy(q[:, 0], q[:, 1], q[:, 2], q[:, 3])
+    np.testing.assert_allclose(out, np.stack([r, p, y], 1), rtol=0, atol=1e-14)

@@ -1,0 +1,354 @@
+"""bench.py -- env-steps/s of the batched WaypointQuadEnv step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rollout|step] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over the whole env batch.  Workloads (BASELINE.json `configs`):
+  rollout  configs[3]/[4]: v2 env, 1,048,576 envs per GPU, float32: MlpPolicy rollout forward (weights of the
+           reference's checkpoints_from_8_6M/ppo_model_2300000_steps.zip) -> sample -> clip -> env step
+           (physics + reward + termination + obs) -> auto-reset.  Default.
+  step     configs[2]-style: the env step alone on pre-generated uniform-random actions.
+Envs are independent, so N GPUs run N shards with no data-path collective (weak scaling); the only
+collective is the max-over-ranks of the timing.
+
+Printed JSON (one line, rank 0): the base contract + `roofline` (dominant kernel vs measured HBM peak),
+`cpu_baseline` (the CPU oracle port of the reference step on the host cores), `e2e` (same metric through
+the SB3-style VecEnv call with pinned host buffers, copies inside the timed region), `clocks`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+ALGO_BYTES = {("v2", "f32"): 269, ("v2", "f64"): 425, ("v1", "f32"): 249}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference step on the host cores
+# --------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, n_env, seconds = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+
+    from oracle import quad_oracle as qo
+
+    rng = np.random.default_rng(seed)
+    vec = qo.VecOracle("v2", n_env, lambda ids, eps: rng.random((len(ids), qo.N_UNIFORMS)), integrator="lsoda")
+    vec.reset()
+    lo, hi = np.array([0, -1, -1, -1.0]), np.array([2, 1, 1, 1.0])
+    done_steps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        a = (lo + (hi - lo) * rng.random((n_env, 4))).astype(np.float32)
+        with np.errstate(all="ignore"):
+            vec.step(a)
+        done_steps += n_env
+    return done_steps, time.perf_counter() - t0
+
+
+def cpu_baseline(seconds: float = 12.0, n_env: int = 8, procs: int | None = None) -> dict:
+    """v2 step + auto-reset, uniform-random float32 actions, scipy LSODA like the reference; one process per core."""
+    import multiprocessing as mp
+
+    cores = procs or (os.cpu_count() or 1)
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, n_env, seconds) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    longest = max(r[1] for r in res)
+    return {"value": total / longest, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{total} env-steps of v2 (float64, scipy LSODA like quadcopter.py:113, auto-reset, uniform-random "
+                      f"float32 actions) by oracle/quad_oracle.py, {cores} processes x {n_env} envs for {seconds:.0f} s "
+                      f"(wall {wall:.1f} s)"}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(seconds=per_step)
+    t0 = time.perf_counter()
+    base = None
+    for _ in range(args.steps):
+        base = cpu_baseline(seconds=per_step)
+        vals.append(base["value"])
+    ms = (time.perf_counter() - t0) * 1e3 / max(1, args.steps)
+    value = statistics.mean(vals)
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "note": "CPU oracle port of the reference step (the reference tree is not on the GPU box); "
+                       "each step = one bounded sample on all host cores"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                power.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_hbm_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/roofline_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel_key)
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+def workload_name(args) -> str:
+    n = args.n_envs
+    tag = f"{n // (1 << 20)}M" if n % (1 << 20) == 0 else str(n)
+    return f"v2_{args.workload}_{tag}_{args.precision}"
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n_envs                     # per GPU: weak scaling, one shard per rank
+    env = BatchedQuadEnv(n, env_version=2, precision=args.precision, integrator="rk4", substeps=args.substeps,
+                         device=local, env_id_offset=rank * n, seed=args.seed)
+    env.reset()
+    launches_per_step = 1
+    policy = None
+    if args.workload == "rollout":
+        from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+        policy = MlpPolicyKernel.from_npz(os.path.join(ROOT, "tests", "golden", "policy_v2.npz"), device=dev)
+        launches_per_step = 2
+    # uniform-random actions over the action box, pre-generated ring (step workload) / sampling noise (rollout)
+    g = torch.Generator(device=dev).manual_seed(args.seed + rank)
+    lo = torch.tensor([0.0, -1, -1, -1], device=dev)
+    hi = torch.tensor([2.0, 1, 1, 1], device=dev)
+    ring = [(lo + (hi - lo) * torch.rand((n, 4), device=dev, generator=g)).contiguous() for _ in range(4)]
+    noise = [torch.randn((n, 4), device=dev, generator=g) for _ in range(4)] if policy else None
+    act_lo, act_hi = lo, hi
+
+    def one_step(i):
+        if policy is None:
+            env.step(ring[i & 3])
+        else:
+            policy.forward(env.obs, noise[i & 3], clip_low=act_lo, clip_high=act_hi)   # -> policy.actions_clipped
+            env.step(policy.actions_clipped)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        if policy is not None:
+            policy.forward(env.obs, noise[i & 3], clip_low=act_lo, clip_high=act_hi)
+            step_events[i][0].record()
+            env.step(policy.actions_clipped)
+            step_events[i][1].record()
+        else:
+            step_events[i][0].record()
+            env.step(ring[i & 3])
+            step_events[i][1].record()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in step_events)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = n * world * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the SB3-style VecEnv call: pinned host actions in, obs/reward/done out --------
+    from rl_aerial_manipulator_b200.vec_env import QuadVecEnv
+    env.close()
+    del ring
+    venv = QuadVecEnv(n, env_version=2, precision=args.precision, substeps=args.substeps, device=local, seed=args.seed,
+                      env_id_offset=rank * n, info_mode="lazy")
+    obs = venv.reset()
+    rng = np.random.default_rng(args.seed + rank)
+    host_actions = [(np.array([0, -1, -1, -1.0]) + np.array([2, 2, 2, 2.0]) * rng.random((n, 4))).astype(np.float32) for _ in range(2)]
+    e2e_steps = max(3, min(args.steps, 30))
+
+    def e2e_step(i):
+        nonlocal obs
+        if policy is not None:
+            a = policy.predict_host(obs, stochastic=True)          # obs H2D -> forward -> clipped actions D2H
+        else:
+            a = host_actions[i & 1]
+        obs, rew, dones, infos = venv.step(a)
+        return float(rew[0])
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = n * world * e2e_steps / e2e_s
+    h2d = venv.h2d_bytes_per_step + (n * venv.sim.obs_dim * 4 if policy is not None else 0)
+    d2h = venv.d2h_bytes_per_step + (n * 4 * 4 if policy is not None else 0)
+    venv.close()
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        algo = ALGO_BYTES[("v2", args.precision)]
+        achieved = algo * n / (step_kernel_ms / 1e3) / 1e9
+        kname = f"env_step_kernel<{'float' if args.precision == 'f32' else 'double'},v2,rk4>"
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(kname), "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo,
+                    "kernel_ms": step_kernel_ms}
+        base = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], capture_output=True, text=True)
+            try:
+                base = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception:  # noqa: BLE001
+                base = {"error": (r.stderr or r.stdout)[-300:]}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": workload_name(args), "envs_per_gpu": n, "envs_total": n * world, "integrator": f"rk4x{args.substeps}",
+                           "actions": "policy (ppo_model_2300000_steps weights, stochastic, clipped)" if policy else "uniform-random over the action box, 4 pre-generated device buffers",
+                           "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
+                           "parallelism": f"env-shard x{world}, no data-path collective"},
+                "roofline": roofline, "cpu_baseline": base,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                        "api": "QuadVecEnv.step(actions: np.ndarray) -> obs, rewards, dones, infos (pinned staging, info_mode=lazy)"},
+                "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=["rollout", "step"])
+    ap.add_argument("--n-envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--substeps", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "rollout" if os.path.exists(os.path.join(ROOT, "rl-aerial-manipulator_b200", "policy.py")) else "step"
+    if args.cpu_baseline_only:
+        print(json.dumps(cpu_baseline()), flush=True)
+        return
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,30 +149,45 @@ int qs_reset_uniforms(qs_handle* h, const int64_t* env_ids, const int32_t* episo
 int qs_lsoda_stats(qs_handle* h, int32_t* counters_out, double* steps_out, void* stream);
 
 /* VecNormalize --------------------------------------------------------------------------------------
- * Replaces stable_baselines3 VecNormalize(norm_obs=True) / RunningMeanStd.update
- * (call sites initial-implementation-v1/rl_train_vecN.py:11, rl_checkpoint_train_vecN.py:23-28).
- * stats layout (device, f64): [0]=count, [1..d]=mean, [1+d..2d]=var.
+ * Replaces stable_baselines3 VecNormalize(norm_obs=True, norm_reward=False) / RunningMeanStd.update
+ * (call sites initial-implementation-v1/rl_train_vecN.py:11, rl_checkpoint_train_vecN.py:23-28, runsim_vecN.py:24-26;
+ * field layout pinned by initial-implementation-v1/vec_normalize.pkl).
+ * stats layout (device, f64): [0]=count, [1..d]=mean, [1+d..2d]=var  -- RunningMeanStd(mean, var, count).
  */
-/* batch moments of x f32[n,d] -> moments f64[1+2d] = (n, mean[d], M2[d]) ; scratch: f64[qs_moments_scratch_len(d)] */
+/* batch moments of x f32[n,d] -> moments f64[1+2d] = (n, mean[d], M2[d]); scratch: f64[qs_moments_scratch_len(d)].
+ * The triplet is what ranks all-gather (NCCL) before qs_vecnorm_merge. */
 int64_t qs_moments_scratch_len(int d);
 int qs_batch_moments(const float* x, int64_t n, int d, double* moments_out, double* scratch, void* stream);
-/* merge `k` moment triplets f64[k,1+2d] (e.g. all-gathered over ranks) into the running stats (Chan et al.) */
+/* running stats <- Chan merge of `k` moment triplets f64[k,1+2d] (RunningMeanStd.update_from_moments, k batches) */
 int qs_vecnorm_merge(double* stats, const double* moments, int k, int d, void* stream);
-/* out = clip((x - mean) / sqrt(var + eps), +-clip) as f32; out may alias x */
+/* out = clip((x - mean) / sqrt(var + eps), +-clip) as f32 (VecNormalize.normalize_obs); out may alias x */
 int qs_vecnorm_apply(const float* x, float* out, int64_t n, int d, const double* stats, double eps, double clip,
                      void* stream);
+/* returns = returns*gamma + reward; snapshot <- returns (what ret_rms.update sees); returns[done] = 0
+ * (VecNormalize.step_wait).  reward is f32[n] or f64[n]; flags u8[n] are qs_step's. */
+int qs_returns_update(float* returns, const void* reward, int reward_is_f64, const uint8_t* flags, float gamma,
+                      int64_t n, float* snapshot, void* stream);
+const char* qs_vecnorm_last_error(void);
 
 /* MlpPolicy rollout forward -----------------------------------------------------------------------
  * Replaces stable_baselines3 ActorCriticPolicy.forward for MlpPolicy(net_arch=[128,64,64], Tanh)
- * (PPO("MlpPolicy", ...) at initial-implementation-v2/rl_train.py:27-53, v1/rl_train_vecN.py:13-33).
- * params: one f32 device blob, layout given by qs_policy_param_offsets() (actor trunk, critic trunk, heads, log_std).
- *   obs      f32[n,d]
- *   noise    f32[n,4] standard normal, or NULL for deterministic actions (mean)
- *   actions  f32[n,4]  (unclipped, what SB3 stores)     values f32[n]     logp f32[n]
+ * (PPO("MlpPolicy", ...) at initial-implementation-v2/rl_train.py:27-53, v1/rl_train_vecN.py:13-33) and, with
+ * noise == NULL, ActorCriticPolicy.predict(deterministic=True) (runsim_scaledObs.py:54).
+ * params: one f32 device blob of qs_policy_param_count(obs_dim) floats; per net (actor, then critic), weights
+ * input-major (W^T of torch's [out,in]):  W1[obs][128] b1[128] W2[128][64] b2[64] W3[64][64] b3[64] Wh[64][4] bh[4]
+ * (the critic uses column 0 of Wh / bh[0]); then log_std[4].
+ *   obs        f32[n,d]
+ *   noise      f32[n,4] standard normal, or NULL for deterministic actions (the mean)
+ *   norm_stats f64[1+2d] VecNormalize stats applied to obs on load, or NULL; obs_norm_out f32[n,d] or NULL
+ *   actions    f32[n,4] unclipped (what SB3 stores)    actions_clipped f32[n,4] or NULL (clip_lo/clip_hi f32[4], host)
+ *   values f32[n]    logp f32[n]
  */
 int64_t qs_policy_param_count(int obs_dim);
 int qs_policy_forward(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
-                      float* actions, float* values, float* logp, void* stream);
+                      const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out,
+                      float* actions, float* actions_clipped, const float* clip_lo, const float* clip_hi,
+                      float* values, float* logp, void* stream);
+const char* qs_policy_last_error(void);
 
 #ifdef __cplusplus
 }

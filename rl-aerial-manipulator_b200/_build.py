@@ -17,7 +17,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libquadsim.so")
+# QS_NVCC_DEFINES="-DX=1 ..." + QS_LIB_TAG=foo build an experimental variant lib/libquadsim_foo.so (A/B runs on the GPU box;
+# load it with QS_LIB_PATH).  The product build uses neither.
+TAG = os.environ.get("QS_LIB_TAG", "")
+DEFINES = os.environ.get("QS_NVCC_DEFINES", "").split()
+OBJ = OBJ + ("_" + TAG if TAG else "")
+LIB = os.path.join(LIBDIR, f"libquadsim{'_' + TAG if TAG else ''}.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -46,7 +51,7 @@ def _newest_header() -> float:
 
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [nvcc(), *ARCH, *COMMON, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [nvcc(), *ARCH, *COMMON, *DEFINES, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as f:

@@ -14,7 +14,7 @@ import numpy as np
 from . import params
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libquadsim.so")
+LIB_PATH = os.environ.get("QS_LIB_PATH") or os.path.join(HERE, "lib", "libquadsim.so")
 
 QS_ABI_VERSION = 1
 QS_F32, QS_F64 = 0, 1

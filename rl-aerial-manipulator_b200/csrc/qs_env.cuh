@@ -303,6 +303,24 @@ QS_HD uint32_t step_logic(EnvState<Real, VER>& s, Real& reward_out, int& ep_len)
 // reset: consumes the unit uniforms of (seed, global env id, episode) in the reference's draw order.
 //   uniform(lo,hi) = lo + (hi-lo)*u ; rand() = u ; randint(lo,hi) = lo + floor(u*(hi-lo))
 // ------------------------------------------------------------------------------------------------
+// lo + (hi - lo) * u with the product and the sum rounded separately (NumPy's uniform()); on the device the
+// _rn intrinsics keep nvcc from contracting them into one FMA, which would change the last bit.
+QS_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+QS_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+QS_HD double uniform_rn(double lo, double hi, double u) { return add_rn(lo, mul_rn(hi - lo, u)); }
+
 template <typename Real, int VER>
 QS_HD void reset_env(EnvState<Real, VER>& s, const ResetConsts& rc, uint64_t seed, uint64_t env_gid) {
     constexpr int NWP = EnvState<Real, VER>::NWP;
@@ -311,10 +329,10 @@ QS_HD void reset_env(EnvState<Real, VER>& s, const ResetConsts& rc, uint64_t see
     reset_uniforms(seed, env_gid, s.episode, u);
     int k = 0;
     double start[3];
-    start[0] = -1.0 + 2.0 * u[k++];
-    start[1] = -1.0 + 2.0 * u[k++];
+    start[0] = uniform_rn(-1.0, 1.0, u[k++]);
+    start[1] = uniform_rn(-1.0, 1.0, u[k++]);
     k++;                                  // third component of uniform(-1,1,3): drawn, then overwritten
-    start[2] = 1.0 + 1.0 * u[k++];
+    start[2] = uniform_rn(1.0, 2.0, u[k++]);
 #pragma unroll
     for (int i = 0; i < 13; ++i) s.y[i] = Real(0);
     s.y[0] = (Real)start[0];
@@ -337,36 +355,36 @@ QS_HD void reset_env(EnvState<Real, VER>& s, const ResetConsts& rc, uint64_t see
         double w[3];
         if (kind <= 1) {
             double end[3];
-            end[0] = -1.0 + 2.0 * u[k++];
-            end[1] = -1.0 + 2.0 * u[k++];
+            end[0] = uniform_rn(-1.0, 1.0, u[k++]);
+            end[1] = uniform_rn(-1.0, 1.0, u[k++]);
             k++;
-            end[2] = 0.5 + 2.5 * u[k++];
+            end[2] = uniform_rn(0.5, 3.0, u[k++]);
             int axis = -1;
             if (kind == 1) axis = 2 - (int)floor(u[k++] * 3.0);   // randint(0,3): 0 -> z, 1 -> y, 2 -> x
             const double t = 1.0;                                   // i / num_waypoints, i = 1
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                w[i] = start[i] + t * (end[i] - start[i]);
-                if (kind == 1 && i == axis) w[i] = w[i] + rc.sin_tab[0];   // + sin(2*t*pi)
+                w[i] = add_rn(start[i], mul_rn(t, end[i] - start[i]));
+                if (kind == 1 && i == axis) w[i] = add_rn(w[i], rc.sin_tab[0]);   // + sin(2*t*pi)
             }
             if (kind == 1) w[2] = fmax(w[2], 0.2);
         } else {
-            w[0] = start[0] + 0.8 * rc.cos_tab[0];
-            w[1] = start[1] + 0.8 * rc.sin_tab[0];
-            w[2] = fmax(start[2] + 1 * 0.4, 0.2);
+            w[0] = add_rn(start[0], mul_rn(0.8, rc.cos_tab[0]));
+            w[1] = add_rn(start[1], mul_rn(0.8, rc.sin_tab[0]));
+            w[2] = fmax(add_rn(start[2], 1 * 0.4), 0.2);
         }
         s.wp[0][0] = (Real)w[0];
         s.wp[0][1] = (Real)w[1];
         s.wp[0][2] = (Real)w[2];
-        s.final_yaw = (Real)(-PI + (PI - (-PI)) * u[k++]);
+        s.final_yaw = (Real)uniform_rn(-PI, PI, u[k++]);
     } else {
         nwp = 1 + (int)floor(u[k++] * 2.0);                         // randint(1,3)
 #pragma unroll
         for (int j = 0; j < NWP; ++j) {
             if (j < nwp) {
-                s.wp[j][0] = (Real)(-1.0 + 2.0 * u[k++]);
-                s.wp[j][1] = (Real)(-1.0 + 2.0 * u[k++]);
-                s.wp[j][2] = (Real)(1.0 + 2.0 * u[k++]);
+                s.wp[j][0] = (Real)uniform_rn(-1.0, 1.0, u[k++]);
+                s.wp[j][1] = (Real)uniform_rn(-1.0, 1.0, u[k++]);
+                s.wp[j][2] = (Real)uniform_rn(1.0, 3.0, u[k++]);
             }
         }
     }

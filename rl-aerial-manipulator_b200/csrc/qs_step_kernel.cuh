@@ -41,6 +41,13 @@ struct StepParams {
 
 #if defined(__CUDACC__)
 constexpr int STEP_BLOCK = 128;
+// resident CTAs per SM the float32/RK4 kernel is compiled for (caps registers at 65536/(128*N)); measured on
+// B200 -- see profiles/r01/step_minblocks.md.  float64 and LSODA need the registers more than the occupancy.
+#ifndef QS_STEP_MINB_F32
+#define QS_STEP_MINB_F32 5
+#endif
+template <typename Real, int INTEG> struct StepOcc { static constexpr int MINB = 1; };
+template <> struct StepOcc<float, 0> { static constexpr int MINB = QS_STEP_MINB_F32; };
 
 // Row-major [32, OBS] tile of one warp -> global, 128 bits per lane per store.
 template <int OBS>
@@ -65,7 +72,7 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, const f
 }
 
 template <typename Real, int VER, int INTEG>
-__global__ void __launch_bounds__(STEP_BLOCK) env_step_kernel(const StepParams<Real> p) {
+__global__ void __launch_bounds__(STEP_BLOCK, StepOcc<Real, INTEG>::MINB) env_step_kernel(const StepParams<Real> p) {
     constexpr int OBS = EnvTraits<VER>::OBS;
     __shared__ float s_tile[STEP_BLOCK / 32][32 * (OBS + 1)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -1,0 +1,184 @@
+"""VecNormalize running statistics on the device (csrc/qs_vecnorm.cu), sharded over GPUs with one NCCL
+all-gather of 2D+1 doubles per update.
+
+Replaces stable_baselines3 `VecNormalize(env, norm_obs=True, norm_reward=False)` as used by the reference
+(initial-implementation-v1/rl_train_vecN.py:11, rl_checkpoint_train_vecN.py:23-28; saved state
+initial-implementation-v1/vec_normalize.pkl: obs_rms / ret_rms with mean, var, count; clip_obs=10,
+gamma=0.99, epsilon=1e-8).
+
+  DeviceRunningMeanStd   RunningMeanStd: stats tensor f64[1+2d] = (count, mean, var) living on the GPU
+  DeviceVecNormalize     tensor-API wrapper around BatchedQuadEnv: step() -> normalised obs, statistics
+                         updated on device, merged across ranks when torch.distributed is initialised
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from ._cabi import load_library
+
+
+def _bind(lib):
+    if getattr(lib, "_vn_bound", False):
+        return
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.qs_moments_scratch_len.argtypes = [C.c_int]
+    lib.qs_moments_scratch_len.restype = i64
+    lib.qs_batch_moments.argtypes = [vp, i64, C.c_int, vp, vp, vp]
+    lib.qs_vecnorm_merge.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    lib.qs_vecnorm_apply.argtypes = [vp, vp, i64, C.c_int, vp, C.c_double, C.c_double, vp]
+    lib.qs_returns_update.argtypes = [vp, vp, C.c_int, vp, C.c_float, i64, vp, vp]
+    for f in ("qs_batch_moments", "qs_vecnorm_merge", "qs_vecnorm_apply", "qs_returns_update"):
+        getattr(lib, f).restype = C.c_int
+    lib.qs_vecnorm_last_error.restype = C.c_char_p
+    lib._vn_bound = True
+
+
+def merge_moments(stats, moments):
+    """Host restatement of qs_vecnorm_merge / RunningMeanStd.update_from_moments for float64 numpy or torch
+    CPU tensors: stats (count, mean[d], var[d]) <- merge of triplets (n, mean[d], M2[d]).  Used by the gloo tests."""
+    d = (stats.shape[0] - 1) // 2
+    count, mean, var = stats[0].clone(), stats[1:1 + d].clone(), stats[1 + d:].clone()
+    for m in moments.reshape(-1, 1 + 2 * d):
+        bn = m[0]
+        if bn <= 0:
+            continue
+        delta = m[1:1 + d] - mean
+        tot = count + bn
+        mean = mean + delta * bn / tot
+        M2 = var * count + m[1 + d:] + delta * delta * count * bn / tot
+        var = M2 / tot
+        count = tot
+    return torch.cat([count.reshape(1), mean, var])
+
+
+class DeviceRunningMeanStd:
+    """stable_baselines3.common.running_mean_std.RunningMeanStd on the device."""
+
+    def __init__(self, dim: int, device, epsilon: float = 1e-4, group=None):
+        self.lib = load_library()
+        _bind(self.lib)
+        self.dim, self.device, self.group = int(dim), torch.device(device), group
+        self.stats = torch.zeros(1 + 2 * dim, dtype=torch.float64, device=self.device)
+        self.stats[0] = epsilon
+        self.stats[1 + dim:] = 1.0
+        self._scratch = torch.empty(int(self.lib.qs_moments_scratch_len(dim)), dtype=torch.float64, device=self.device)
+        self._moments = torch.zeros(1 + 2 * dim, dtype=torch.float64, device=self.device)
+        self._gathered = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.qs_vecnorm_last_error().decode()}")
+
+    @property
+    def count(self):
+        return self.stats[0]
+
+    @property
+    def mean(self):
+        return self.stats[1:1 + self.dim]
+
+    @property
+    def var(self):
+        return self.stats[1 + self.dim:]
+
+    def batch_moments(self, x: torch.Tensor) -> torch.Tensor:
+        x2 = x.reshape(x.shape[0], -1)
+        assert x2.dtype == torch.float32 and x2.is_contiguous() and x2.shape[1] == self.dim
+        self._check(self.lib.qs_batch_moments(C.c_void_p(x2.data_ptr()), x2.shape[0], self.dim, C.c_void_p(self._moments.data_ptr()),
+                                              C.c_void_p(self._scratch.data_ptr()), self._stream()), "qs_batch_moments")
+        return self._moments
+
+    def update(self, x: torch.Tensor) -> None:
+        """RunningMeanStd.update(x) for the batch sharded over all ranks of `group` (or this GPU alone)."""
+        m = self.batch_moments(x)
+        k = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            k = dist.get_world_size(self.group)
+            if self._gathered is None:
+                self._gathered = torch.empty((k, 1 + 2 * self.dim), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(self._gathered, m, group=self.group)   # 2d+1 doubles per rank over NVLink
+            m = self._gathered
+        self._check(self.lib.qs_vecnorm_merge(C.c_void_p(self.stats.data_ptr()), C.c_void_p(m.data_ptr()), k, self.dim, self._stream()),
+                    "qs_vecnorm_merge")
+
+    def normalize(self, x: torch.Tensor, out: torch.Tensor | None = None, epsilon: float = 1e-8, clip: float = 10.0) -> torch.Tensor:
+        x2 = x.reshape(x.shape[0], -1)
+        if out is None:
+            out = torch.empty_like(x2)
+        self._check(self.lib.qs_vecnorm_apply(C.c_void_p(x2.data_ptr()), C.c_void_p(out.data_ptr()), x2.shape[0], self.dim,
+                                              C.c_void_p(self.stats.data_ptr()), epsilon, clip, self._stream()), "qs_vecnorm_apply")
+        return out.reshape(x.shape)
+
+
+class DeviceVecNormalize:
+    """VecNormalize over a BatchedQuadEnv, everything on the device.
+
+    step(actions) -> StepOut whose `.obs` is the normalised observation; `raw_obs` keeps the env's own.
+    `training=False` freezes the statistics (evaluation, runsim).
+    """
+
+    def __init__(self, env, norm_obs: bool = True, norm_reward: bool = False, clip_obs: float = 10.0, clip_reward: float = 10.0,
+                 gamma: float = 0.99, epsilon: float = 1e-8, training: bool = True, group=None):
+        self.env, self.norm_obs, self.norm_reward = env, norm_obs, norm_reward
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon, self.training = clip_obs, clip_reward, gamma, epsilon, training
+        dev, n, d = env.device, env.n_envs, env.obs_dim
+        self.obs_rms = DeviceRunningMeanStd(d, dev, group=group)
+        self.ret_rms = DeviceRunningMeanStd(1, dev, group=group)
+        self.returns = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._ret_snapshot = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.norm_obs_buf = torch.empty((n, d), dtype=torch.float32, device=dev)
+        self.norm_terminal_obs = torch.empty((n, d), dtype=torch.float32, device=dev)
+        self.lib = self.obs_rms.lib
+
+    def reset(self) -> torch.Tensor:
+        obs = self.env.reset()
+        self.returns.zero_()
+        if self.training and self.norm_obs:
+            self.obs_rms.update(obs)
+        return self.obs_rms.normalize(obs, self.norm_obs_buf, self.epsilon, self.clip_obs) if self.norm_obs else obs
+
+    def step(self, actions: torch.Tensor):
+        out = self.env.step(actions)
+        self.raw_obs = out.obs
+        if self.training:
+            if self.norm_obs:
+                self.obs_rms.update(out.obs)
+            # `returns = returns*gamma + reward; ret_rms.update(returns); returns[dones] = 0` (runs even with norm_reward=False)
+            rc = self.lib.qs_returns_update(C.c_void_p(self.returns.data_ptr()), C.c_void_p(out.reward.data_ptr()),
+                                            int(out.reward.dtype == torch.float64), C.c_void_p(out.flags.data_ptr()), self.gamma,
+                                            self.env.n_envs, C.c_void_p(self._ret_snapshot.data_ptr()), self.obs_rms._stream())
+            self.obs_rms._check(rc, "qs_returns_update")
+            self.ret_rms.update(self._ret_snapshot)
+        if self.norm_obs:
+            out.obs = self.obs_rms.normalize(out.obs, self.norm_obs_buf, self.epsilon, self.clip_obs)
+            out.terminal_obs = self.obs_rms.normalize(out.terminal_obs, self.norm_terminal_obs, self.epsilon, self.clip_obs)
+        if self.norm_reward:
+            out.reward = torch.clamp(out.reward / torch.sqrt(self.ret_rms.var[0] + self.epsilon), -self.clip_reward, self.clip_reward)
+        return out
+
+    def state_dict(self) -> dict:
+        """Field names of stable_baselines3's pickled VecNormalize (see tests/golden/vecnorm_v1.npz)."""
+        g = lambda t: t.detach().cpu().numpy().copy()
+        return {"obs_mean": g(self.obs_rms.mean), "obs_var": g(self.obs_rms.var), "obs_count": float(self.obs_rms.count),
+                "ret_mean": float(self.ret_rms.mean[0]), "ret_var": float(self.ret_rms.var[0]), "ret_count": float(self.ret_rms.count),
+                "clip_obs": self.clip_obs, "clip_reward": self.clip_reward, "gamma": self.gamma, "epsilon": self.epsilon,
+                "norm_obs": self.norm_obs, "norm_reward": self.norm_reward}
+
+    def load_state_dict(self, sd: dict) -> None:
+        d = self.env.obs_dim
+        dev = self.env.device
+        self.obs_rms.stats[0] = float(sd["obs_count"])
+        self.obs_rms.stats[1:1 + d] = torch.as_tensor(sd["obs_mean"], dtype=torch.float64, device=dev)
+        self.obs_rms.stats[1 + d:] = torch.as_tensor(sd["obs_var"], dtype=torch.float64, device=dev)
+        self.ret_rms.stats[0] = float(sd["ret_count"])
+        self.ret_rms.stats[1] = float(sd["ret_mean"])
+        self.ret_rms.stats[2] = float(sd["ret_var"])
+        for k in ("clip_obs", "clip_reward", "gamma", "epsilon"):
+            if k in sd:
+                setattr(self, k, float(sd[k]))

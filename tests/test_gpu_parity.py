@@ -322,8 +322,10 @@ def test_properties_1M_envs_f32():
     lo = torch.tensor([0.0, -1, -1, -1], device="cuda")
     hi = torch.tensor([2.0, 1, 1, 1], device="cuda")
     ep_done = torch.zeros(n, dtype=torch.int64, device="cuda")
-    for t in range(60):
+    n_steps = 200
+    for t in range(n_steps):
         a = lo + (hi - lo) * torch.rand((n, 4), device="cuda", generator=g)
+        a[: n // 2, 0] *= 0.25                                      # half the envs sink and crash -> auto-reset
         out = env.step(a)
         ep_done += out.done
         assert torch.isfinite(out.obs).all() and torch.isfinite(out.reward).all()
@@ -332,16 +334,17 @@ def test_properties_1M_envs_f32():
     st = env.get_state(["episode", "current_step", "y"])
     assert torch.equal(st["episode"].long(), ep_done)              # one reset per done, nothing else resets
     assert int(ep_done.sum()) > 0
-    assert (st["current_step"] <= 60).all() and (st["y"][:, 2] > -1).all()
+    assert int(ep_done[: n // 2].sum()) > n // 4
+    assert (st["current_step"] <= n_steps).all() and (st["y"][:, 2] > -1).all()
     env.close()
 
 
 def test_determinism_and_shard_independence():
     """Same seed -> same rollout; a batch split over two handles with env_id_offset draws the same episodes."""
-    n, steps = 8192, 40
+    n, steps = 8192, 200
     g = torch.Generator(device="cuda").manual_seed(1)
-    acts = [torch.rand((n, 4), device="cuda", generator=g) * torch.tensor([2.0, 2, 2, 2], device="cuda") - torch.tensor([0.0, 1, 1, 1], device="cuda")
-            for _ in range(steps)]
+    acts = [torch.rand((n, 4), device="cuda", generator=g) * torch.tensor([0.6, 2, 2, 2], device="cuda") - torch.tensor([0.0, 1, 1, 1], device="cuda")
+            for _ in range(steps)]   # low thrust: every env crashes and is auto-reset at least once
 
     def run(n_envs, offset, sl):
         env = make_env(n_envs, "v2", precision="f32", seed=21, env_id_offset=offset)
@@ -364,7 +367,7 @@ def test_determinism_and_shard_independence():
     assert torch.equal(torch.cat([lo[0], hi[0]], 1), full[0])
     assert torch.equal(torch.cat([lo[1], hi[1]], 1), full[1])
     assert torch.equal(torch.cat([lo[2], hi[2]], 0), full[2])
-    assert int(full[1].sum()) > 0
+    assert int(full[1].sum()) > n // 2
 
 
 @pytest.mark.parametrize("n", [1, 31, 33, 257])

@@ -1,0 +1,143 @@
+"""GPU tests of the VecNormalize and MlpPolicy kernels through the C-ABI, against the SB3 restatement
+(oracle/sb3_oracle.py), a plain torch fp32 reference and the golden forward outputs (tests/golden/policy_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sb3_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("tag,obs_dim", [("v2", 20), ("v1", 17)])
+def test_policy_forward_matches_golden_and_torch(golden_dir, tag, obs_dim):
+    from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+    z = np.load(os.path.join(golden_dir, f"policy_{tag}.npz"))
+    pol = MlpPolicyKernel.from_npz(os.path.join(golden_dir, f"policy_{tag}.npz"), device="cuda")
+    assert pol.obs_dim == obs_dim
+    obs = torch.from_numpy(z["obs"]).cuda()
+    a, v, lp = pol.forward(obs)                                   # deterministic: actions == mean
+    # golden: torch CPU forward of the shipped SB3 weights; float32 kernel vs float64 truth, and vs float32 truth
+    np.testing.assert_allclose(t2n(a), z["mean_f64"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(t2n(v), z["value_f64"], rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(t2n(a), z["mean_f32"], rtol=2e-5, atol=2e-5)
+    log_std = z["w.log_std"]
+    np.testing.assert_allclose(t2n(lp), np.full(len(z["obs"]), -log_std.sum() - 2 * np.log(2 * np.pi)), rtol=1e-6)
+    lo, hi = np.array([0, -1, -1, -1.0]), np.array([2, 1, 1, 1.0])
+    np.testing.assert_array_equal(t2n(pol.actions_clipped), np.clip(t2n(a), lo, hi).astype(np.float32))
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 4099, 262144])
+def test_policy_forward_stochastic_vs_oracle(golden_dir, n):
+    from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+    pol = MlpPolicyKernel.from_npz(os.path.join(golden_dir, "policy_v2.npz"), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(n)
+    obs = torch.randn((n, 20), device="cuda", generator=g) * 0.7
+    noise = torch.randn((n, 4), device="cuda", generator=g)
+    a, v, lp = pol.forward(obs, noise)
+    m = min(n, 4096)
+    ao, vo, lpo, _ = so.mlp_policy_forward(pol.state_dict, t2n(obs[:m]), t2n(noise[:m]))
+    np.testing.assert_allclose(t2n(a[:m]), ao, rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(t2n(v[:m]), vo, rtol=3e-5, atol=3e-4)
+    np.testing.assert_allclose(t2n(lp[:m]), lpo, rtol=1e-5, atol=1e-5)
+    # whole batch against the plain torch fp32 reference of the same op
+    mean_t, value_t = pol.torch_reference(obs)
+    a_t = mean_t + torch.exp(torch.from_numpy(pol.state_dict["log_std"]).cuda()) * noise
+    assert (a - a_t).abs().max() < 5e-5 and (v - value_t).abs().max() < 5e-4
+
+
+def test_policy_forward_with_fused_vecnormalize(golden_dir):
+    from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+    from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd
+    pol = MlpPolicyKernel.from_npz(os.path.join(golden_dir, "policy_v2.npz"), device="cuda")
+    n = 10000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.randn((n, 20), device="cuda", generator=g) * 3 + 1
+    rms = DeviceRunningMeanStd(20, "cuda")
+    rms.update(obs)
+    normed = rms.normalize(obs)
+    a1, v1, _ = pol.forward(normed)
+    a1, v1 = a1.clone(), v1.clone()
+    out = torch.empty_like(obs)
+    a2, v2, _ = pol.forward(obs, norm_stats=rms.stats, obs_norm_out=out)
+    assert torch.allclose(out, normed, atol=1e-6)
+    assert torch.allclose(a1, a2, atol=1e-5) and torch.allclose(v1, v2, atol=1e-4)
+
+
+@pytest.mark.parametrize("d,n", [(20, 1 << 20), (17, 100003), (1, 65536), (20, 8), (20, 1)])
+def test_batch_moments_and_running_update(d, n):
+    from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd
+    g = torch.Generator(device="cuda").manual_seed(d * 7 + n)
+    rms = DeviceRunningMeanStd(d, "cuda")
+    ref64 = so.RunningMeanStd((d,), dtype_batch=np.float64)
+    ref32 = so.RunningMeanStd((d,), dtype_batch=np.float32)
+    for it in range(3):
+        x = torch.randn((n, d), device="cuda", generator=g) * (1 + it) + torch.arange(d, device="cuda") * 0.5
+        x[:, 0] = 1.0 + 1e-4 * torch.randn(n, device="cuda", generator=g)       # a nearly constant column (quaternion w)
+        m = t2n(rms.batch_moments(x))
+        xn = t2n(x).astype(np.float64)
+        assert m[0] == n
+        np.testing.assert_allclose(m[1:1 + d], xn.mean(0), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(m[1 + d:], xn.var(0) * n, rtol=1e-9, atol=1e-12)
+        rms.update(x)
+        ref64.update(xn)
+        ref32.update(t2n(x))
+        s = t2n(rms.stats)
+        assert abs(s[0] - ref64.count) < 1e-9
+        np.testing.assert_allclose(s[1:1 + d], ref64.mean, rtol=1e-12, atol=1e-12)     # float64 restatement: exact arithmetic
+        np.testing.assert_allclose(s[1 + d:], ref64.var, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(s[1:1 + d], ref32.mean, rtol=1e-4, atol=1e-4)      # SB3's float32 batch statistics
+        np.testing.assert_allclose(s[1 + d:], ref32.var, rtol=1e-3, atol=1e-6)
+        out = t2n(rms.normalize(x))
+        want = np.clip((xn - ref64.mean) / np.sqrt(ref64.var + 1e-8), -10, 10)
+        np.testing.assert_allclose(out, want, rtol=2e-5, atol=2e-5)
+
+
+def test_device_vecnormalize_rollout_vs_oracle():
+    """DeviceVecNormalize around the float64 env vs the SB3 restatement fed the same obs / rewards / dones."""
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    from rl_aerial_manipulator_b200.vec_normalize import DeviceVecNormalize
+    n = 512
+    env = BatchedQuadEnv(n, env_version=1, precision="f64", integrator="rk4", obs_scaled=False, seed=3)   # rl_env.py + VecNormalize
+    vn = DeviceVecNormalize(env, gamma=0.99)
+    ref = so.VecNormalizeOracle(n, 17, gamma=0.99)
+    obs = vn.reset()
+    np.testing.assert_allclose(t2n(obs), ref.reset(t2n(env.obs)), rtol=2e-5, atol=2e-5)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(150):
+        a = torch.rand((n, 4), device="cuda", generator=g) * torch.tensor([0.8, 2, 2, 2], device="cuda") - torch.tensor([0, 1, 1, 1.0], device="cuda")
+        out = vn.step(a.float())
+        want = ref.step(t2n(vn.raw_obs), t2n(out.reward), t2n(out.done))
+        np.testing.assert_allclose(t2n(out.obs), want, rtol=3e-5, atol=3e-5)
+    sd = vn.state_dict()
+    np.testing.assert_allclose(sd["obs_mean"], ref.obs_rms.mean, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(sd["obs_var"], ref.obs_rms.var, rtol=1e-8, atol=1e-12)
+    assert abs(sd["obs_count"] - ref.obs_rms.count) < 1e-6 and abs(sd["ret_count"] - ref.ret_rms.count) < 1e-6
+    np.testing.assert_allclose(sd["ret_mean"], ref.ret_rms.mean, rtol=1e-5, atol=1e-5)      # returns are carried in float32 on the device
+    np.testing.assert_allclose(sd["ret_var"], ref.ret_rms.var, rtol=1e-4)
+    assert int(out.done.sum()) >= 0 and sd["obs_count"] > 151 * n
+
+
+def test_vecnormalize_pkl_layout_roundtrip(golden_dir):
+    """The reference's vec_normalize.pkl snapshot (17-D float64 mean/var, count 2031632.0001) loads into the device object."""
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    from rl_aerial_manipulator_b200.vec_normalize import DeviceVecNormalize
+    z = np.load(os.path.join(golden_dir, "vecnorm_v1.npz"))
+    env = BatchedQuadEnv(64, env_version=1, precision="f32", obs_scaled=False)
+    vn = DeviceVecNormalize(env, training=False)
+    vn.load_state_dict({k: z[k] for k in z.files})
+    sd = vn.state_dict()
+    np.testing.assert_array_equal(sd["obs_mean"], z["obs_mean"])
+    np.testing.assert_array_equal(sd["obs_var"], z["obs_var"])
+    assert sd["obs_count"] == float(z["obs_count"]) == 2031632.0001 and sd["clip_obs"] == 10.0 and sd["gamma"] == 0.99
+    obs = vn.reset()
+    raw = t2n(env.obs).astype(np.float64)
+    want = np.clip((raw - z["obs_mean"]) / np.sqrt(z["obs_var"] + 1e-8), -10, 10)
+    np.testing.assert_allclose(t2n(obs), want, rtol=2e-5, atol=2e-5)
+    assert float(vn.obs_rms.count) == 2031632.0001     # training=False: statistics frozen

@@ -204,10 +204,17 @@ def run_gpu(args) -> None:
     env.reset()
     launches_per_step = 1
     policy = None
+    vn = None
     if args.workload == "rollout":
         from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+        from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd
         policy = MlpPolicyKernel.from_npz(os.path.join(ROOT, "tests", "golden", "policy_v2.npz"), device=dev)
         launches_per_step = 2
+        if args.vecnorm:
+            # VecNormalize(norm_obs=True): moments of this rank's shard -> all-gather of 2D+1 doubles over NCCL (N>1)
+            # -> Chan merge on device -> normalisation fused into the policy kernel's obs load
+            vn = DeviceRunningMeanStd(env.obs_dim, dev)
+            launches_per_step = 5
     # uniform-random actions over the action box, pre-generated ring (step workload) / sampling noise (rollout)
     g = torch.Generator(device=dev).manual_seed(args.seed + rank)
     lo = torch.tensor([0.0, -1, -1, -1], device=dev)
@@ -216,11 +223,16 @@ def run_gpu(args) -> None:
     noise = [torch.randn((n, 4), device=dev, generator=g) for _ in range(4)] if policy else None
     act_lo, act_hi = lo, hi
 
+    def policy_step(i):
+        if vn is not None:
+            vn.update(env.obs)
+        policy.forward(env.obs, noise[i & 3], norm_stats=vn.stats if vn is not None else None)   # -> policy.actions_clipped
+
     def one_step(i):
         if policy is None:
             env.step(ring[i & 3])
         else:
-            policy.forward(env.obs, noise[i & 3], clip_low=act_lo, clip_high=act_hi)   # -> policy.actions_clipped
+            policy_step(i)
             env.step(policy.actions_clipped)
 
     def barrier():
@@ -238,7 +250,7 @@ def run_gpu(args) -> None:
     ev0.record()
     for i in range(args.steps):
         if policy is not None:
-            policy.forward(env.obs, noise[i & 3], clip_low=act_lo, clip_high=act_hi)
+            policy_step(i)
             step_events[i][0].record()
             env.step(policy.actions_clipped)
             step_events[i][1].record()
@@ -271,7 +283,7 @@ def run_gpu(args) -> None:
     def e2e_step(i):
         nonlocal obs
         if policy is not None:
-            a = policy.predict_host(obs, stochastic=True)          # obs H2D -> forward -> clipped actions D2H
+            a = policy.predict_host(obs, stochastic=True, norm_stats=vn.stats if vn is not None else None)  # obs H2D -> forward -> actions D2H
         else:
             a = host_actions[i & 1]
         obs, rew, dones, infos = venv.step(a)
@@ -313,6 +325,7 @@ def run_gpu(args) -> None:
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": workload_name(args), "envs_per_gpu": n, "envs_total": n * world, "integrator": f"rk4x{args.substeps}",
+                           "vecnormalize": bool(vn is not None),
                            "actions": "policy (ppo_model_2300000_steps weights, stochastic, clipped)" if policy else "uniform-random over the action box, 4 pre-generated device buffers",
                            "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
                            "parallelism": f"env-shard x{world}, no data-path collective"},
@@ -336,6 +349,7 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--substeps", type=int, default=1)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--vecnorm", type=int, default=1, help="rollout workload: update VecNormalize statistics every step (NCCL all-gather when N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -118,15 +118,15 @@ __global__ void __launch_bounds__(POLICY_THREADS, 1) policy_forward_ffma_kernel(
     float* sHa = sX + OBS * RS;                    // per half: [128][RS] (H1, later H3) and [64][RS] (H2)
     constexpr int HALF_FLOATS = H1 * RS + H2 * RS;
     float* sOut = sHa + 2 * HALF_FLOATS;           // [TILE][8]: 4 means, value
-    __shared__ float s_mean[32], s_istd[32];
+    __shared__ double s_mean[32], s_istd[32];   // float64 like SB3's normalize_obs (see qs_vecnorm.cu)
 
     const int tid = threadIdx.x;
     for (int i = tid; i < L.total(); i += POLICY_THREADS) sP[i] = __ldg(p.params + i);
     if (tid < OBS) {
-        float m = 0.f, is = 1.f;
+        double m = 0.0, is = 1.0;
         if (p.norm) {
-            m = (float)p.norm[1 + tid];
-            is = (float)(1.0 / sqrt(p.norm[1 + OBS + tid] + (double)p.norm_eps));
+            m = p.norm[1 + tid];
+            is = 1.0 / sqrt(p.norm[1 + OBS + tid] + (double)p.norm_eps);
         }
         s_mean[tid] = m;
         s_istd[tid] = is;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(POLICY_THREADS, 1) policy_forward_ffma_kernel(
             if (e < valid) {
                 x = __ldcs(p.obs + e0 * OBS + i);
                 if (p.norm) {
-                    x = (x - s_mean[k]) * s_istd[k];
+                    x = (float)(((double)x - s_mean[k]) * s_istd[k]);
                     x = fminf(fmaxf(x, -p.norm_clip), p.norm_clip);
                     if (p.obs_norm_out) p.obs_norm_out[e0 * OBS + i] = x;
                 }

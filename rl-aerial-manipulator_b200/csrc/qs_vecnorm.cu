@@ -12,7 +12,9 @@
 // Kernels:
 //   moments_partial  per-CTA column sums in float64 of (x - shift) and (x - shift)^2; block size is a multiple
 //                    of lcm(32, d) so a thread keeps one column while striding through the row-major [n,d]
-//                    batch with coalesced loads; warp-shuffle + shared-memory reduction inside the CTA
+//                    batch with coalesced loads; shared-memory reduction inside the CTA (the lanes of a warp hold
+//                    different columns -- 32 consecutive floats of a row-major [n,20] batch -- so a shuffle tree
+//                    would need a transposing layout that un-coalesces the loads)
 //   moments_final    fixed-order sum of the CTA partials -> (n, mean[d], M2[d]); this triplet is what ranks
 //                    all-gather over NCCL (2d+1 doubles) -- Chan's merge is associative
 //   merge            running stats <- merge of k triplets (one per rank), on device, no host sync
@@ -94,10 +96,12 @@ __global__ void vecnorm_merge_kernel(double* __restrict__ stats, const double* _
 
 __global__ void vecnorm_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t total, int d,
                                      const double* __restrict__ stats, float eps, float clip) {
-    __shared__ float s_mean[32], s_istd[32];
+    // SB3 subtracts the float64 mean from the float32 obs in float64 and only casts the result; with a nearly
+    // constant column (quaternion w ~ 1, std ~ 1e-4) a float32 subtraction would lose 3 digits
+    __shared__ double s_mean[32], s_istd[32];
     if (threadIdx.x < d) {
-        s_mean[threadIdx.x] = (float)stats[1 + threadIdx.x];
-        s_istd[threadIdx.x] = (float)(1.0 / sqrt(stats[1 + d + threadIdx.x] + (double)eps));
+        s_mean[threadIdx.x] = stats[1 + threadIdx.x];
+        s_istd[threadIdx.x] = 1.0 / sqrt(stats[1 + d + threadIdx.x] + (double)eps);
     }
     __syncthreads();
     const bool vec = (total % 4 == 0) && ((((uintptr_t)x | (uintptr_t)out) & 15) == 0);
@@ -109,7 +113,7 @@ __global__ void vecnorm_apply_kernel(const float* __restrict__ x, float* __restr
             int c = (int)((i * 4) % d);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                pv[j] = fminf(fmaxf((pv[j] - s_mean[c]) * s_istd[c], -clip), clip);
+                pv[j] = fminf(fmaxf((float)(((double)pv[j] - s_mean[c]) * s_istd[c]), -clip), clip);
                 c = c + 1 == d ? 0 : c + 1;
             }
             reinterpret_cast<float4*>(out)[i] = v;
@@ -117,7 +121,7 @@ __global__ void vecnorm_apply_kernel(const float* __restrict__ x, float* __restr
     } else {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
             const int c = (int)(i % d);
-            out[i] = fminf(fmaxf((x[i] - s_mean[c]) * s_istd[c], -clip), clip);
+            out[i] = fminf(fmaxf((float)(((double)x[i] - s_mean[c]) * s_istd[c]), -clip), clip);
         }
     }
 }

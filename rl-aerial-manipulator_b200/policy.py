@@ -62,6 +62,8 @@ class MlpPolicyKernel:
         _bind(self.lib)
         self.obs_dim = int(obs_dim)
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.state_dict = {k: np.asarray(v, dtype=np.float32) for k, v in state_dict.items()}
         blob = pack_params(self.state_dict, self.obs_dim)
         assert blob.size == self.lib.qs_policy_param_count(self.obs_dim)

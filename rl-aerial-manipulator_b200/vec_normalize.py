@@ -61,6 +61,8 @@ class DeviceRunningMeanStd:
         self.lib = load_library()
         _bind(self.lib)
         self.dim, self.device, self.group = int(dim), torch.device(device), group
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.stats = torch.zeros(1 + 2 * dim, dtype=torch.float64, device=self.device)
         self.stats[0] = epsilon
         self.stats[1 + dim:] = 1.0

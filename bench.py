@@ -197,6 +197,7 @@ def run_gpu(args) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     n = args.n_envs                     # per GPU: weak scaling, one shard per rank
     env = BatchedQuadEnv(n, env_version=2, precision=args.precision, integrator="rk4", substeps=args.substeps,

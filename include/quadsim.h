@@ -181,12 +181,22 @@ const char* qs_vecnorm_last_error(void);
  *   norm_stats f64[1+2d] VecNormalize stats applied to obs on load, or NULL; obs_norm_out f32[n,d] or NULL
  *   actions    f32[n,4] unclipped (what SB3 stores)    actions_clipped f32[n,4] or NULL (clip_lo/clip_hi f32[4], host)
  *   values f32[n]    logp f32[n]
+ *   impl       QS_POLICY_FP32: CUDA-core FFMA kernel, float32 throughout;
+ *              QS_POLICY_TENSOR: tcgen05/TMEM kernel, split-float16 operands (hi+lo, 3 MMAs per k-step) + float32
+ *                                accumulation: float32-level accuracy (values within 2e-3 of float64 on |V| <= 2800);
+ *              QS_POLICY_TENSOR_FAST: tcgen05/TMEM kernel, single float16 operands + MUFU.TANH (means within 3e-2,
+ *                                values within ~1e-2 |V|max);
+ *              QS_POLICY_AUTO: TENSOR for n >= 16384, FP32 below
  */
+#define QS_POLICY_AUTO 0
+#define QS_POLICY_FP32 1
+#define QS_POLICY_TENSOR 2
+#define QS_POLICY_TENSOR_FAST 3
 int64_t qs_policy_param_count(int obs_dim);
 int qs_policy_forward(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
                       const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out,
                       float* actions, float* actions_clipped, const float* clip_lo, const float* clip_hi,
-                      float* values, float* logp, void* stream);
+                      float* values, float* logp, int impl, void* stream);
 const char* qs_policy_last_error(void);
 
 #ifdef __cplusplus

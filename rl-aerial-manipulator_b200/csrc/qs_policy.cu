@@ -225,6 +225,12 @@ static size_t policy_smem_bytes(int obs) {
 
 thread_local char g_policy_error[256] = "";
 
+// tensor-core path (qs_policy_tc.cu): precise = split-float16 (float32 accuracy), else single float16
+int launch_policy_tc(int precise, const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
+                     const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out, float* actions,
+                     float* actions_clipped, const float* clip_lo, const float* clip_hi, float* values, float* logp,
+                     cudaStream_t stream, const char** err_out);
+
 }  // namespace qs
 
 using namespace qs;
@@ -238,12 +244,25 @@ const char* qs_policy_last_error(void) { return g_policy_error; }
 int qs_policy_forward(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
                       const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out,
                       float* actions, float* actions_clipped, const float* clip_lo, const float* clip_hi,
-                      float* values, float* logp, void* stream) {
+                      float* values, float* logp, int impl, void* stream) {
     if (!params || !obs || !actions || !values || !logp || n < 0 || (obs_dim != 17 && obs_dim != 20)) {
         snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward: bad argument (obs_dim must be 17 or 20)");
         return QS_EINVAL;
     }
     if (n == 0) return QS_OK;
+    if (impl < 0 || impl > 3) {
+        snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward: impl must be QS_POLICY_AUTO, _FP32, _TENSOR or _TENSOR_FAST");
+        return QS_EINVAL;
+    }
+    // QS_POLICY_AUTO: the tcgen05 kernel (float32-accurate split-float16 mode) wins once there are enough 128-env tiles
+    // to fill the SMs (profiles/r01/policy_paths.md); below that the FFMA kernel's finer 64-env tiles do
+    if (impl == QS_POLICY_TENSOR || impl == QS_POLICY_TENSOR_FAST || (impl == QS_POLICY_AUTO && n >= 16384)) {
+        const char* msg = nullptr;
+        const int rc = launch_policy_tc(impl != QS_POLICY_TENSOR_FAST, params, obs_dim, obs, noise, n, norm_stats, norm_eps, norm_clip,
+                                        obs_norm_out, actions, actions_clipped, clip_lo, clip_hi, values, logp, (cudaStream_t)stream, &msg);
+        if (rc != QS_OK && msg) snprintf(g_policy_error, sizeof(g_policy_error), "%s", msg);
+        return rc;
+    }
     PolicyArgs a;
     a.params = params; a.obs = obs; a.noise = noise; a.norm = norm_stats; a.obs_norm_out = obs_norm_out;
     a.actions = actions; a.actions_clipped = actions_clipped; a.values = values; a.logp = logp; a.n = n;

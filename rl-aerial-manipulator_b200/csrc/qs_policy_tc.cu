@@ -1,0 +1,455 @@
+// qs_policy_tc.cu -- MlpPolicy rollout forward on tcgen05 with the activations kept in TENSOR MEMORY (A operand from
+// TMEM, "TS" form of tcgen05.mma) and, in PRECISE mode, split-float16 arithmetic that reproduces float32 accuracy.
+//
+// Same operator as qs_policy.cu (SB3 ActorCriticPolicy.forward for MlpPolicy [128,64,64] Tanh;
+// reference call sites initial-implementation-v2/rl_train.py:27-53, initial-implementation-v1/rl_train_vecN.py:13-33).
+//
+// Why: single-pass float16 operands put the value head ~0.7 rms (max ~9) away from the float32 forward because the
+// shipped critic has head weights up to 70 (sum |w| = 4000).  Splitting every operand x = hi + lo (two float16, 22
+// significant bits) and issuing three MMAs per k-step (hi*hi + hi*lo + lo*hi, float32 accumulation in TMEM) brings the
+// error to ~1e-3 on |V| <= 2800 -- the same as torch's own float32 forward -- while the tensor pipe stays far from
+// saturated (the kernel is bound by the epilogue's MUFU work, not by MMA issue).
+//
+// Layout: one persistent CTA per SM, two independent 128-thread groups, one 128-env tile per group (UMMA M=128, one env
+// per TMEM lane and per thread).  Shared memory holds only the weights (float16 hi and lo, canonical K-major no-swizzle
+// core-matrix layout: offset(row, kchunk) = kchunk*rows*16 + row*16 bytes, LBO = rows*16, SBO = 128) and the float32
+// biases/heads.  Per group 256 TMEM columns:
+//     [  0,128)  layer-1 accumulator, overwritten IN PLACE by its own activations: each 32-column float32 chunk a thread
+//                reads becomes 16 columns of packed hi + 16 columns of packed lo (the A operand of layer 2);
+//                later reused as the layer-3 accumulator
+//     [128,192)  layer-2 accumulator -> in place -> A operand of layer 3
+//     [224,256)  observation tile, hi | lo  (A operand of layer 1, kept for both nets)
+// so hidden activations never touch shared memory: tcgen05.ld -> registers -> bias, tanh, split -> tcgen05.st.
+#include "../../include/quadsim.h"
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace qs {
+namespace tc {
+
+constexpr int ROWS = 128, GROUPS = 2, THREADS = ROWS * GROUPS;
+constexpr int K1 = 32;
+constexpr int N1 = 128, N2 = 64, N3 = 64, NACT = 4;
+constexpr int W1_BYTES = (K1 / 8) * N1 * 16, W2_BYTES = (N1 / 8) * N2 * 16, W3_BYTES = (N2 / 8) * N3 * 16;
+constexpr int W_SET = 2 * (W1_BYTES + W2_BYTES + W3_BYTES);          // both nets, one precision part: 65536
+constexpr int OFF_W1 = 0, OFF_W2 = 2 * W1_BYTES, OFF_W3 = OFF_W2 + 2 * W2_BYTES;
+constexpr int C_B1 = 0, C_B2 = C_B1 + 2 * N1, C_B3 = C_B2 + 2 * N2, C_WH = C_B3 + 2 * N3, C_BH = C_WH + 2 * N3 * NACT,
+              C_LS = C_BH + 2 * NACT, C_TOTAL = C_LS + NACT;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t COL_R1 = 0, COL_R2 = 128, COL_X = 224;
+
+struct Blob {
+    int obs;
+    __host__ __device__ int per_net() const { return obs * N1 + N1 + N1 * N2 + N2 + N2 * N3 + N3 + N3 * NACT + NACT; }
+    __host__ __device__ int w1(int net) const { return net * per_net(); }
+    __host__ __device__ int b1(int net) const { return w1(net) + obs * N1; }
+    __host__ __device__ int w2(int net) const { return b1(net) + N1; }
+    __host__ __device__ int b2(int net) const { return w2(net) + N1 * N2; }
+    __host__ __device__ int w3(int net) const { return b2(net) + N2; }
+    __host__ __device__ int b3(int net) const { return w3(net) + N2 * N3; }
+    __host__ __device__ int wh(int net) const { return b3(net) + N3; }
+    __host__ __device__ int bh(int net) const { return wh(net) + N3 * NACT; }
+    __host__ __device__ int log_std() const { return 2 * per_net(); }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_exact(float x) {   // 1 - 2/(exp(2x)+1): ex2.approx + rcp.approx, abs error ~1e-7
+    const float t = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, t + 1.0f);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// (a, b) -> packed hi halves and packed lo halves, a = hi_a + lo_a to ~22 bits
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_h2(a - hf.x, b - hf.y);
+}
+
+struct Args {
+    const float* params;
+    const float* obs;
+    const float* noise;
+    const double* norm;
+    float* obs_norm_out;
+    float* actions;
+    float* actions_clipped;
+    float* values;
+    float* logp;
+    int64_t n;
+    float norm_eps, norm_clip;
+    float lo[4], hi[4];
+};
+
+// weights [K][N] float32 (input-major blob) -> float16 hi (and lo) canonical B operands [N rows][KP], zero padded
+template <bool PRECISE>
+__device__ __forceinline__ void stage_weights(const float* __restrict__ w, int K, int KP, int N, unsigned char* dst_hi,
+                                              unsigned char* dst_lo, int tid) {
+    for (int i = tid; i < (KP / 8) * N; i += THREADS) {
+        const int c = i / N, n = i - c * N;
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k0 = c * 8 + 2 * j, k1 = k0 + 1;
+            const float a = k0 < K ? __ldg(w + (int64_t)k0 * N + n) : 0.f;
+            const float b = k1 < K ? __ldg(w + (int64_t)k1 * N + n) : 0.f;
+            split_h2(a, b, ph[j], pl[j]);
+        }
+        *reinterpret_cast<uint4*>(dst_hi + (size_t)i * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (PRECISE) *reinterpret_cast<uint4*>(dst_lo + (size_t)i * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+}
+
+// one 32-column accumulator chunk of this thread's row -> +bias -> tanh (float32 in y)
+template <bool PRECISE>
+__device__ __forceinline__ void act32(uint32_t taddr, const float* __restrict__ bias, float* y) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float pre = __uint_as_float(v[i]) + bias[i];
+        y[i] = PRECISE ? tanh_exact(pre) : tanh_mufu(pre);
+    }
+}
+
+// y[32] -> packed float16 hi (16 columns at taddr) and, if PRECISE, lo (16 columns at taddr + 16): in place over the chunk
+template <bool PRECISE>
+__device__ __forceinline__ void put32(uint32_t taddr, const float* y) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) split_h2(y[2 * j], y[2 * j + 1], h[j], l[j]);
+    tmem_st16(taddr, h);
+    if (PRECISE) tmem_st16(taddr + 16, l);
+}
+
+// all MMAs of one layer: K elements from TMEM chunks of 32 (hi at +0, lo at +16), weights at wb_hi / wb_lo
+template <bool PRECISE>
+__device__ __forceinline__ void issue_layer(uint32_t d_col, uint32_t a_col, int K, uint32_t wb_hi, uint32_t wb_lo, uint32_t b_lbo, int N) {
+    const uint32_t idesc = make_idesc(N);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+        const uint32_t a_hi = a_col + 32u * (ks >> 1) + 8u * (ks & 1);
+        const uint64_t bh = make_desc(wb_hi + ks * 2 * b_lbo, b_lbo, 128);
+        umma_ts(d_col, a_hi, bh, idesc, acc);
+        acc = 1;
+        if (PRECISE) {
+            const uint64_t bl = make_desc(wb_lo + ks * 2 * b_lbo, b_lbo, 128);
+            umma_ts(d_col, a_hi, bl, idesc, 1);
+            umma_ts(d_col, a_hi + 16u, bh, idesc, 1);
+        }
+    }
+}
+
+template <int OBS, bool PRECISE>
+__global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Args p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ __align__(8) uint64_t s_bars[2];
+    __shared__ double s_mean[32], s_istd[32];
+    constexpr int OFF_LO = W_SET;                                 // lo parts follow the hi parts
+    constexpr int OFF_CONST = PRECISE ? 2 * W_SET : W_SET;
+    const int tid = threadIdx.x;
+    const int g = tid >> 7, t = tid & 127, warp = tid >> 5;
+    const Blob B{OBS};
+    float* sC = reinterpret_cast<float*>(smem + OFF_CONST);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bars[0]), 1);
+        mbar_init(smem_u32(&s_bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int net = 0; net < 2; ++net) {
+        stage_weights<PRECISE>(p.params + B.w1(net), OBS, K1, N1, smem + OFF_W1 + net * W1_BYTES, smem + OFF_LO + OFF_W1 + net * W1_BYTES, tid);
+        stage_weights<PRECISE>(p.params + B.w2(net), N1, N1, N2, smem + OFF_W2 + net * W2_BYTES, smem + OFF_LO + OFF_W2 + net * W2_BYTES, tid);
+        stage_weights<PRECISE>(p.params + B.w3(net), N2, N2, N3, smem + OFF_W3 + net * W3_BYTES, smem + OFF_LO + OFF_W3 + net * W3_BYTES, tid);
+        for (int i = tid; i < N1; i += THREADS) sC[C_B1 + net * N1 + i] = __ldg(p.params + B.b1(net) + i);
+        for (int i = tid; i < N2; i += THREADS) sC[C_B2 + net * N2 + i] = __ldg(p.params + B.b2(net) + i);
+        for (int i = tid; i < N3; i += THREADS) sC[C_B3 + net * N3 + i] = __ldg(p.params + B.b3(net) + i);
+        for (int i = tid; i < N3 * NACT; i += THREADS) sC[C_WH + net * N3 * NACT + i] = __ldg(p.params + B.wh(net) + i);
+        if (tid < NACT) sC[C_BH + net * NACT + tid] = __ldg(p.params + B.bh(net) + tid);
+    }
+    if (tid < NACT) sC[C_LS + tid] = __ldg(p.params + B.log_std() + tid);
+    if (tid < OBS) {
+        double m = 0.0, is = 1.0;
+        if (p.norm) {
+            m = p.norm[1 + tid];
+            is = 1.0 / sqrt(p.norm[1 + OBS + tid] + (double)p.norm_eps);
+        }
+        s_mean[tid] = m;
+        s_istd[tid] = is;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base + (uint32_t)g * 256u;             // this group's 256 columns (lane field 0)
+    const uint32_t lane_addr = tmem + ((uint32_t)(t & ~31) << 16);     // this warp's lane quadrant
+    const uint32_t bar = smem_u32(&s_bars[g]);
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t phase = 0;
+    constexpr uint32_t B1_LBO = N1 * 16, B2_LBO = N2 * 16;
+
+    const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
+    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + g; tile < n_tiles; tile += (int64_t)gridDim.x * GROUPS) {
+        const int64_t e = tile * ROWS + t;
+        const bool live = e < p.n;
+        {   // observation row -> (normalise) -> split float16 -> TMEM columns [224,256)
+            float x[K1];
+#pragma unroll
+            for (int k = 0; k < K1; ++k) x[k] = 0.f;
+            if (live) {
+                const float* row = p.obs + e * OBS;
+#pragma unroll
+                for (int k = 0; k < OBS; ++k) x[k] = __ldcs(row + k);
+                if (p.norm) {
+#pragma unroll
+                    for (int k = 0; k < OBS; ++k) {
+                        float v = (float)(((double)x[k] - s_mean[k]) * s_istd[k]);
+                        x[k] = fminf(fmaxf(v, -p.norm_clip), p.norm_clip);
+                    }
+                    if (p.obs_norm_out) {
+                        float* orow = p.obs_norm_out + e * OBS;
+#pragma unroll
+                        for (int k = 0; k < OBS; ++k) orow[k] = x[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < OBS; ++k) x[k] = fminf(fmaxf(x[k], -60000.f), 60000.f);   // float16 range
+            }
+            put32<PRECISE>(lane_addr + COL_X, x);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        group_bar(g);
+
+        float mean[NACT] = {0.f, 0.f, 0.f, 0.f};
+        float value = 0.f;
+#pragma unroll 1
+        for (int net = 0; net < 2; ++net) {
+            // ---------------- layer 1: X[128 x 32] . W1^T -> R1[128 columns]
+            if (t == 0) {
+                tc_fence_after();
+                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_X, K1, sbase + OFF_W1 + net * W1_BYTES, sbase + OFF_LO + OFF_W1 + net * W1_BYTES, B1_LBO, N1);
+                umma_commit(bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < N1 / 32; ++cb) {
+                float y[32];
+                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, sC + C_B1 + net * N1 + cb * 32, y);
+                put32<PRECISE>(lane_addr + COL_R1 + cb * 32, y);        // in place: hi | lo
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            group_bar(g);
+            // ---------------- layer 2: H1[128 x 128] . W2^T -> R2[64 columns]
+            if (t == 0) {
+                tc_fence_after();
+                issue_layer<PRECISE>(tmem + COL_R2, tmem + COL_R1, N1, sbase + OFF_W2 + net * W2_BYTES, sbase + OFF_LO + OFF_W2 + net * W2_BYTES, B2_LBO, N2);
+                umma_commit(bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < N2 / 32; ++cb) {
+                float y[32];
+                act32<PRECISE>(lane_addr + COL_R2 + cb * 32, sC + C_B2 + net * N2 + cb * 32, y);
+                put32<PRECISE>(lane_addr + COL_R2 + cb * 32, y);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            group_bar(g);
+            // ---------------- layer 3: H2[128 x 64] . W3^T -> R1[first 64 columns], then the float32 head
+            if (t == 0) {
+                tc_fence_after();
+                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_R2, N2, sbase + OFF_W3 + net * W3_BYTES, sbase + OFF_LO + OFF_W3 + net * W3_BYTES, B2_LBO, N3);
+                umma_commit(bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            __syncwarp();
+            tc_fence_after();
+            float o[NACT];
+#pragma unroll
+            for (int j = 0; j < NACT; ++j) o[j] = sC[C_BH + net * NACT + j];
+#pragma unroll 1
+            for (int cb = 0; cb < N3 / 32; ++cb) {
+                float y[32];
+                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, sC + C_B3 + net * N3 + cb * 32, y);
+                const float4* wh = reinterpret_cast<const float4*>(sC + C_WH + net * N3 * NACT + cb * 32 * NACT);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float4 w = wh[k];
+                    o[0] = fmaf(y[k], w.x, o[0]);
+                    o[1] = fmaf(y[k], w.y, o[1]);
+                    o[2] = fmaf(y[k], w.z, o[2]);
+                    o[3] = fmaf(y[k], w.w, o[3]);
+                }
+            }
+            if (net == 0) {
+#pragma unroll
+                for (int j = 0; j < NACT; ++j) mean[j] = o[j];
+            } else {
+                value = o[0];
+            }
+            tc_fence_before();   // the next MMAs overwrite TMEM columns this thread has just read
+            group_bar(g);
+        }
+        if (live) {
+            const float ls[4] = {sC[C_LS], sC[C_LS + 1], sC[C_LS + 2], sC[C_LS + 3]};
+            float4 eps = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.noise) eps = __ldcs(reinterpret_cast<const float4*>(p.noise) + e);
+            float4 a;
+            a.x = fmaf(__expf(ls[0]), eps.x, mean[0]);
+            a.y = fmaf(__expf(ls[1]), eps.y, mean[1]);
+            a.z = fmaf(__expf(ls[2]), eps.z, mean[2]);
+            a.w = fmaf(__expf(ls[3]), eps.w, mean[3]);
+            const float HALF_LOG_2PI = 0.9189385332046727f;
+            const float lp = -0.5f * (eps.x * eps.x + eps.y * eps.y + eps.z * eps.z + eps.w * eps.w) - (ls[0] + ls[1] + ls[2] + ls[3]) -
+                             4.0f * HALF_LOG_2PI;
+            reinterpret_cast<float4*>(p.actions)[e] = a;
+            if (p.actions_clipped) {
+                float4 c;
+                c.x = fminf(fmaxf(a.x, p.lo[0]), p.hi[0]);
+                c.y = fminf(fmaxf(a.y, p.lo[1]), p.hi[1]);
+                c.z = fminf(fmaxf(a.z, p.lo[2]), p.hi[2]);
+                c.w = fminf(fmaxf(a.w, p.lo[3]), p.hi[3]);
+                reinterpret_cast<float4*>(p.actions_clipped)[e] = c;
+            }
+            p.values[e] = value;
+            p.logp[e] = lp;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+}  // namespace tc
+
+thread_local char g_policy_tc_error[256] = "";
+
+template <int OBS, bool PRECISE>
+static cudaError_t launch_one(const tc::Args& a, unsigned grid, cudaStream_t stream) {
+    const int smem = (PRECISE ? 2 : 1) * tc::W_SET + tc::C_TOTAL * 4 + 64;
+    cudaError_t err = cudaFuncSetAttribute(tc::policy_forward_tc_kernel<OBS, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    tc::policy_forward_tc_kernel<OBS, PRECISE><<<grid, tc::THREADS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+int launch_policy_tc(int precise, const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
+                      const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out, float* actions,
+                      float* actions_clipped, const float* clip_lo, const float* clip_hi, float* values, float* logp,
+                      cudaStream_t stream, const char** err_out) {
+    using namespace tc;
+    Args a;
+    a.params = params; a.obs = obs; a.noise = noise; a.norm = norm_stats; a.obs_norm_out = obs_norm_out;
+    a.actions = actions; a.actions_clipped = actions_clipped; a.values = values; a.logp = logp; a.n = n;
+    a.norm_eps = norm_eps; a.norm_clip = norm_clip;
+    for (int i = 0; i < 4; ++i) { a.lo[i] = clip_lo ? clip_lo[i] : -3.4e38f; a.hi[i] = clip_hi ? clip_hi[i] : 3.4e38f; }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (n + ROWS - 1) / ROWS;
+    const int64_t ctas = (tiles + GROUPS - 1) / GROUPS;
+    const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
+    cudaError_t err;
+    if (obs_dim == 20) err = precise ? launch_one<20, true>(a, grid, stream) : launch_one<20, false>(a, grid, stream);
+    else err = precise ? launch_one<17, true>(a, grid, stream) : launch_one<17, false>(a, grid, stream);
+    if (err != cudaSuccess) {
+        snprintf(g_policy_tc_error, sizeof(g_policy_tc_error), "policy_forward_tc_kernel: %s", cudaGetErrorString(err));
+        *err_out = g_policy_tc_error;
+        return QS_ECUDA;
+    }
+    return QS_OK;
+}
+
+}  // namespace qs

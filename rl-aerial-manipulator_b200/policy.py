@@ -31,7 +31,7 @@ def _bind(lib):
     lib.qs_policy_param_count.argtypes = [C.c_int]
     lib.qs_policy_param_count.restype = C.c_int64
     lib.qs_policy_forward.argtypes = [vp, C.c_int, vp, vp, C.c_int64, vp, f32, f32, vp, vp, vp,
-                                      C.POINTER(f32 * 4), C.POINTER(f32 * 4), vp, vp, vp]
+                                      C.POINTER(f32 * 4), C.POINTER(f32 * 4), vp, vp, C.c_int, vp]
     lib.qs_policy_forward.restype = C.c_int
     lib.qs_policy_last_error.restype = C.c_char_p
     lib._policy_bound = True
@@ -56,8 +56,16 @@ def pack_params(sd: dict, obs_dim: int) -> np.ndarray:
     return np.concatenate(parts).astype(np.float32)
 
 
+IMPL = {"auto": 0, "fp32": 1, "tensor": 2, "tensor_fast": 3}
+
+
 class MlpPolicyKernel:
-    def __init__(self, state_dict: dict, obs_dim: int, device):
+    """impl: "fp32" = CUDA-core FFMA kernel (float32 throughout); "tensor" = tcgen05/TMEM kernel with split-float16
+    operands (float32-level accuracy); "tensor_fast" = tcgen05/TMEM, single float16 operands + MUFU.TANH;
+    "auto" = "tensor" for batches >= 16384 envs, "fp32" below."""
+
+    def __init__(self, state_dict: dict, obs_dim: int, device, impl: str = "auto"):
+        self.impl = IMPL[impl]
         self.lib = load_library()
         _bind(self.lib)
         self.obs_dim = int(obs_dim)
@@ -75,18 +83,18 @@ class MlpPolicyKernel:
 
     # ---- constructors ----------------------------------------------------------------------------
     @classmethod
-    def from_npz(cls, path: str, device="cuda"):
+    def from_npz(cls, path: str, device="cuda", impl: str = "auto"):
         z = np.load(path)
         sd = {k[2:]: z[k] for k in z.files if k.startswith("w.")}
-        return cls(sd, sd["mlp_extractor.policy_net.0.weight"].shape[1], device)
+        return cls(sd, sd["mlp_extractor.policy_net.0.weight"].shape[1], device, impl)
 
     @classmethod
-    def from_sb3_zip(cls, path: str, device="cuda"):
+    def from_sb3_zip(cls, path: str, device="cuda", impl: str = "auto"):
         """PPO.load(path) for the policy weights only (`policy.pth` inside the SB3 zip)."""
         with zipfile.ZipFile(path) as z:
             sd = torch.load(io.BytesIO(z.read("policy.pth")), weights_only=True, map_location="cpu")
         sd = {k: v.numpy() for k, v in sd.items()}
-        return cls(sd, sd["mlp_extractor.policy_net.0.weight"].shape[1], device)
+        return cls(sd, sd["mlp_extractor.policy_net.0.weight"].shape[1], device, impl)
 
     # ---- forward ---------------------------------------------------------------------------------
     def _ensure(self, n: int) -> None:
@@ -113,7 +121,8 @@ class MlpPolicyKernel:
             assert norm_stats.dtype == torch.float64 and norm_stats.numel() == 1 + 2 * self.obs_dim
         rc = self.lib.qs_policy_forward(p(self.params), self.obs_dim, p(obs), p(noise), n, p(norm_stats), norm_eps, norm_clip,
                                         p(obs_norm_out), p(self.actions), p(self.actions_clipped), C.byref(self._lo), C.byref(self._hi),
-                                        p(self.values), p(self.logp), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+                                        p(self.values), p(self.logp), self.impl,
+                                        C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"qs_policy_forward failed ({rc}): {self.lib.qs_policy_last_error().decode()}")
         return self.actions, self.values, self.logp

@@ -34,6 +34,7 @@ if ROOT not in sys.path:
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 ALGO_BYTES = {("v2", "f32"): 269, ("v2", "f64"): 425, ("v1", "f32"): 249}
+POLICY_FLOPS = 60032                                                         # actor + critic MACs x 2, v2
 
 
 # --------------------------------------------------------------------------------------------------
@@ -151,14 +152,14 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_hbm_peak() -> tuple[float, str]:
+def measured_peak(key: str, fallback: float) -> tuple[float, str]:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.load(open(p))[key]), f"measured (MEASURED_PEAKS.json {key})"
         except Exception:  # noqa: BLE001
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return fallback, "fallback (B200_PROFILING.md)"
 
 
 def ncu_traffic(kernel_key: str):
@@ -247,11 +248,16 @@ def run_gpu(args) -> None:
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    policy_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     ev0.record()
     for i in range(args.steps):
         if policy is not None:
-            policy_step(i)
+            if vn is not None:
+                vn.update(env.obs)
+            policy_events[i][0].record()
+            policy.forward(env.obs, noise[i & 3], norm_stats=vn.stats if vn is not None else None)
+            policy_events[i][1].record()
             step_events[i][0].record()
             env.step(policy.actions_clipped)
             step_events[i][1].record()
@@ -263,6 +269,7 @@ def run_gpu(args) -> None:
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in step_events)
+    policy_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in policy_events) if policy is not None else None
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -308,13 +315,24 @@ def run_gpu(args) -> None:
     venv.close()
 
     if rank == 0:
-        peak, peak_src = measured_hbm_peak()
+        peak, peak_src = measured_peak("hbm_gbs", 6650.0)
         algo = ALGO_BYTES[("v2", args.precision)]
         achieved = algo * n / (step_kernel_ms / 1e3) / 1e9
         kname = f"env_step_kernel<{'float' if args.precision == 'f32' else 'double'},v2,rk4>"
-        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(kname), "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo,
-                    "kernel_ms": step_kernel_ms}
+        step_roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(kname), "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo,
+                         "kernel_ms": step_kernel_ms}
+        roofline, roofline_other = step_roofline, []
+        if policy is not None and policy_kernel_ms > step_kernel_ms:
+            # the dominant kernel of this workload is the tcgen05 policy forward: algorithmic FLOPs (one float32 pass of the
+            # two MLPs; the split-float16 mode issues 3x that on the tensor pipe) against the measured dense bf16 GEMM rate
+            tpeak, tsrc = measured_peak("bf16_tflops_sustained", 1400.0)
+            tach = POLICY_FLOPS * n / (policy_kernel_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "policy_forward_tc_kernel<20,split-f16>", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
+                        "frac": tach / tpeak, "traffic": ncu_traffic("policy_forward_tc_kernel"), "peak_source": tsrc,
+                        "algorithmic_flops_per_env_step": POLICY_FLOPS, "kernel_ms": policy_kernel_ms,
+                        "note": "epilogue-bound (2 MUFU per tanh, 512 tanh per env): ncu shows the XU pipe, not the tensor pipe, as the limiter"}
+            roofline_other = [step_roofline]
         base = None
         if world == 1 and not args.no_cpu_baseline:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], capture_output=True, text=True)
@@ -330,7 +348,7 @@ def run_gpu(args) -> None:
                            "actions": "policy (ppo_model_2300000_steps weights, stochastic, clipped)" if policy else "uniform-random over the action box, 4 pre-generated device buffers",
                            "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
                            "parallelism": f"env-shard x{world}, no data-path collective"},
-                "roofline": roofline, "cpu_baseline": base,
+                "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": base,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                         "api": "QuadVecEnv.step(actions: np.ndarray) -> obs, rewards, dones, infos (pinned staging, info_mode=lazy)"},
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks}

@@ -10,15 +10,19 @@
 // error to ~1e-3 on |V| <= 2800 -- the same as torch's own float32 forward -- while the tensor pipe stays far from
 // saturated (the kernel is bound by the epilogue's MUFU work, not by MMA issue).
 //
-// Layout: one persistent CTA per SM, two independent 128-thread groups, one 128-env tile per group (UMMA M=128, one env
-// per TMEM lane and per thread).  Shared memory holds only the weights (float16 hi and lo, canonical K-major no-swizzle
+// Layout: one persistent CTA per SM, two independent 256-thread groups, one 128-env tile per group (UMMA M=128, one env
+// per TMEM lane).  Each row is served by two threads (warps w and w+4 of a group share a TMEM lane quadrant) that take
+// alternate 32-column chunks of every epilogue, so 16 warps per SM keep the MUFU pipe fed while the other group's MMAs run.  Shared memory holds only the weights (float16 hi and lo, canonical K-major no-swizzle
 // core-matrix layout: offset(row, kchunk) = kchunk*rows*16 + row*16 bytes, LBO = rows*16, SBO = 128) and the float32
 // biases/heads.  Per group 256 TMEM columns:
 //     [  0,128)  layer-1 accumulator, overwritten IN PLACE by its own activations: each 32-column float32 chunk a thread
 //                reads becomes 16 columns of packed hi + 16 columns of packed lo (the A operand of layer 2);
 //                later reused as the layer-3 accumulator
 //     [128,192)  layer-2 accumulator -> in place -> A operand of layer 3
-//     [224,256)  observation tile, hi | lo  (A operand of layer 1, kept for both nets)
+//     [192,200)  the constant chunk (1, 0, ..., 0): A operand of the bias k-step of layers 2 and 3
+//     [224,256)  observation tile, hi | lo  (A operand of layer 1, kept for both nets); column k = OBS holds 1.0 (bias)
+// In PRECISE mode weights and biases are pre-multiplied by 2*log2(e), so the accumulator IS the exponent of
+// tanh(x) = 1 - 2/(2^acc + 1): the epilogue is MUFU.EX2, FADD, MUFU.RCP, FFMA, then the hi/lo split (LOP3, FADD, 2 F2FP per pair).
 // so hidden activations never touch shared memory: tcgen05.ld -> registers -> bias, tanh, split -> tcgen05.st.
 #include "../../include/quadsim.h"
 #include <cuda_fp16.h>
@@ -29,16 +33,19 @@
 namespace qs {
 namespace tc {
 
-constexpr int ROWS = 128, GROUPS = 2, THREADS = ROWS * GROUPS;
+constexpr int ROWS = 128, GROUPS = 2, GROUP_THREADS = 2 * ROWS, THREADS = GROUP_THREADS * GROUPS;   // two threads per env row
 constexpr int K1 = 32;
 constexpr int N1 = 128, N2 = 64, N3 = 64, NACT = 4;
-constexpr int W1_BYTES = (K1 / 8) * N1 * 16, W2_BYTES = (N1 / 8) * N2 * 16, W3_BYTES = (N2 / 8) * N3 * 16;
+// B operands carry the bias as one extra input: layer 1 uses the spare padding column k = OBS of X (set to 1.0); layers 2/3
+// get one extra k-step of 16 whose A operand is a constant TMEM chunk (1, 0, ..., 0) -- the epilogue adds no bias.
+constexpr int KB = 16;
+constexpr int W1_BYTES = (K1 / 8) * N1 * 16, W2_BYTES = ((N1 + KB) / 8) * N2 * 16, W3_BYTES = ((N2 + KB) / 8) * N3 * 16;
 constexpr int W_SET = 2 * (W1_BYTES + W2_BYTES + W3_BYTES);          // both nets, one precision part: 65536
 constexpr int OFF_W1 = 0, OFF_W2 = 2 * W1_BYTES, OFF_W3 = OFF_W2 + 2 * W2_BYTES;
 constexpr int C_B1 = 0, C_B2 = C_B1 + 2 * N1, C_B3 = C_B2 + 2 * N2, C_WH = C_B3 + 2 * N3, C_BH = C_WH + 2 * N3 * NACT,
               C_LS = C_BH + 2 * NACT, C_TOTAL = C_LS + NACT;
 constexpr int TMEM_COLS = 512;
-constexpr uint32_t COL_R1 = 0, COL_R2 = 128, COL_X = 224;
+constexpr uint32_t COL_R1 = 0, COL_R2 = 128, COL_ONE = 192, COL_X = 224;
 
 struct Blob {
     int obs;
@@ -93,7 +100,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+// Ping-pong between the two groups (the scheme FlashAttention-3 uses for softmax vs GEMM): a group runs an epilogue
+// (MUFU-bound) only while it holds the turn, so the other group's MMA wait / loads / stores fall under it instead of both
+// groups idling the XU pipe at the same moments.  Barrier 3+g is "group g may run its epilogue": g syncs on it, the other
+// group arrives on it when its own epilogue ends.
+__device__ __forceinline__ void turn_wait(int g) { asm volatile("bar.sync %0, 512;" ::"r"(3 + g) : "memory"); }
+__device__ __forceinline__ void turn_pass(int g) { asm volatile("bar.arrive %0, 512;" ::"r"(3 + (g ^ 1)) : "memory"); }
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -122,20 +135,25 @@ __device__ __forceinline__ float tanh_mufu(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float tanh_exact(float x) {   // 1 - 2/(exp(2x)+1): ex2.approx + rcp.approx, abs error ~1e-7
-    const float t = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, t + 1.0f);
+// u = 2*log2(e)*x (the scale lives in the weights): tanh(x) = 1 - 2/(2^u + 1).  ex2.approx/rcp.approx, abs error ~1e-7;
+// u -> +inf gives 1, u -> -inf gives -1 without branches.
+__device__ __forceinline__ float tanh_from_exponent(float u) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(u));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
-// (a, b) -> packed hi halves and packed lo halves, a = hi_a + lo_a to ~22 bits
+// (a, b) -> packed hi halves and packed lo halves, a = hi_a + lo_a to ~21 bits.  hi is the float truncated to float16's
+// 10 explicit mantissa bits (a LOP3, exactly representable), lo the exact remainder rounded to float16.
 __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 hf = __half22float2(h);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = pack_h2(a - hf.x, b - hf.y);
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+    const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+    hi = pack_h2(ah, bh);
+    lo = pack_h2(a - ah, b - bh);
 }
 
 struct Args {
@@ -153,18 +171,19 @@ struct Args {
     float lo[4], hi[4];
 };
 
-// weights [K][N] float32 (input-major blob) -> float16 hi (and lo) canonical B operands [N rows][KP], zero padded
+// weights [K][N] float32 (input-major blob) -> float16 hi (and lo) canonical B operands [N rows][KP], zero padded;
+// input index `kbias` carries the bias (its A element is the constant 1); everything is multiplied by `scale`
 template <bool PRECISE>
-__device__ __forceinline__ void stage_weights(const float* __restrict__ w, int K, int KP, int N, unsigned char* dst_hi,
-                                              unsigned char* dst_lo, int tid) {
+__device__ __forceinline__ void stage_weights(const float* __restrict__ w, const float* __restrict__ bias, int K, int kbias, int KP, int N,
+                                              float scale, unsigned char* dst_hi, unsigned char* dst_lo, int tid) {
     for (int i = tid; i < (KP / 8) * N; i += THREADS) {
         const int c = i / N, n = i - c * N;
         uint32_t ph[4], pl[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k0 = c * 8 + 2 * j, k1 = k0 + 1;
-            const float a = k0 < K ? __ldg(w + (int64_t)k0 * N + n) : 0.f;
-            const float b = k1 < K ? __ldg(w + (int64_t)k1 * N + n) : 0.f;
+            const float a = scale * (k0 < K ? __ldg(w + (int64_t)k0 * N + n) : (k0 == kbias ? __ldg(bias + n) : 0.f));
+            const float b = scale * (k1 < K ? __ldg(w + (int64_t)k1 * N + n) : (k1 == kbias ? __ldg(bias + n) : 0.f));
             split_h2(a, b, ph[j], pl[j]);
         }
         *reinterpret_cast<uint4*>(dst_hi + (size_t)i * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -172,16 +191,17 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ w, int K
     }
 }
 
-// one 32-column accumulator chunk of this thread's row -> +bias -> tanh (float32 in y)
+// one 32-column accumulator chunk of this thread's row (bias already inside) -> tanh (float32 in y)
 template <bool PRECISE>
-__device__ __forceinline__ void act32(uint32_t taddr, const float* __restrict__ bias, float* y) {
+__device__ __forceinline__ void act32(uint32_t taddr, float* y) {
     uint32_t v[32];
     tmem_ld32(taddr, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float pre = __uint_as_float(v[i]) + bias[i];
-        y[i] = PRECISE ? tanh_exact(pre) : tanh_mufu(pre);
-    }
+#ifdef QS_TC_EXPERIMENT_NO_TANH   // timing experiment only: how much of the kernel is XU work
+    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]) * 0.001f;
+#else
+    for (int i = 0; i < 32; ++i) y[i] = PRECISE ? tanh_from_exponent(__uint_as_float(v[i])) : tanh_mufu(__uint_as_float(v[i]));
+#endif
 }
 
 // y[32] -> packed float16 hi (16 columns at taddr) and, if PRECISE, lo (16 columns at taddr + 16): in place over the chunk
@@ -195,10 +215,21 @@ __device__ __forceinline__ void put32(uint32_t taddr, const float* y) {
 }
 
 // all MMAs of one layer: K elements from TMEM chunks of 32 (hi at +0, lo at +16), weights at wb_hi / wb_lo
+// `one_col` != 0: one more k-step whose A operand is the constant chunk (1,0,...) and whose B chunk holds the bias.
 template <bool PRECISE>
-__device__ __forceinline__ void issue_layer(uint32_t d_col, uint32_t a_col, int K, uint32_t wb_hi, uint32_t wb_lo, uint32_t b_lbo, int N) {
+__device__ __forceinline__ void issue_layer(uint32_t d_col, uint32_t a_col, int K, uint32_t wb_hi, uint32_t wb_lo, uint32_t b_lbo, int N,
+                                            uint32_t one_col) {
     const uint32_t idesc = make_idesc(N);
     uint32_t acc = 0;
+#ifdef QS_TC_EXPERIMENT_NO_MMA      // timing experiment only: how much of the kernel is MMA issue + execution
+    return;
+#endif
+    if (one_col) {
+        const int ks = K / 16;
+        umma_ts(d_col, one_col, make_desc(wb_hi + ks * 2 * b_lbo, b_lbo, 128), idesc, 0);
+        if (PRECISE) umma_ts(d_col, one_col, make_desc(wb_lo + ks * 2 * b_lbo, b_lbo, 128), idesc, 1);
+        acc = 1;
+    }
     for (int ks = 0; ks < K / 16; ++ks) {
         const uint32_t a_hi = a_col + 32u * (ks >> 1) + 8u * (ks & 1);
         const uint64_t bh = make_desc(wb_hi + ks * 2 * b_lbo, b_lbo, 128);
@@ -218,10 +249,11 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
     __shared__ uint32_t s_tmem_base;
     __shared__ __align__(8) uint64_t s_bars[2];
     __shared__ double s_mean[32], s_istd[32];
+    __shared__ __align__(16) float s_part[GROUPS][ROWS][NACT];                 // head partial sums of the second thread of each row
     constexpr int OFF_LO = W_SET;                                 // lo parts follow the hi parts
     constexpr int OFF_CONST = PRECISE ? 2 * W_SET : W_SET;
     const int tid = threadIdx.x;
-    const int g = tid >> 7, t = tid & 127, warp = tid >> 5;
+    const int g = tid >> 8, tg = tid & 255, t = tg & 127, half = tg >> 7, warp = tid >> 5;   // t: env row, half: which chunks
     const Blob B{OBS};
     float* sC = reinterpret_cast<float*>(smem + OFF_CONST);
 
@@ -235,12 +267,13 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int net = 0; net < 2; ++net) {
-        stage_weights<PRECISE>(p.params + B.w1(net), OBS, K1, N1, smem + OFF_W1 + net * W1_BYTES, smem + OFF_LO + OFF_W1 + net * W1_BYTES, tid);
-        stage_weights<PRECISE>(p.params + B.w2(net), N1, N1, N2, smem + OFF_W2 + net * W2_BYTES, smem + OFF_LO + OFF_W2 + net * W2_BYTES, tid);
-        stage_weights<PRECISE>(p.params + B.w3(net), N2, N2, N3, smem + OFF_W3 + net * W3_BYTES, smem + OFF_LO + OFF_W3 + net * W3_BYTES, tid);
-        for (int i = tid; i < N1; i += THREADS) sC[C_B1 + net * N1 + i] = __ldg(p.params + B.b1(net) + i);
-        for (int i = tid; i < N2; i += THREADS) sC[C_B2 + net * N2 + i] = __ldg(p.params + B.b2(net) + i);
-        for (int i = tid; i < N3; i += THREADS) sC[C_B3 + net * N3 + i] = __ldg(p.params + B.b3(net) + i);
+        const float sc = PRECISE ? 2.8853900817779268f : 1.0f;     // 2*log2(e): accumulators come out as exponents of 2
+        stage_weights<PRECISE>(p.params + B.w1(net), p.params + B.b1(net), OBS, OBS, K1, N1, sc, smem + OFF_W1 + net * W1_BYTES,
+                               smem + OFF_LO + OFF_W1 + net * W1_BYTES, tid);
+        stage_weights<PRECISE>(p.params + B.w2(net), p.params + B.b2(net), N1, N1, N1 + KB, N2, sc, smem + OFF_W2 + net * W2_BYTES,
+                               smem + OFF_LO + OFF_W2 + net * W2_BYTES, tid);
+        stage_weights<PRECISE>(p.params + B.w3(net), p.params + B.b3(net), N2, N2, N2 + KB, N3, sc, smem + OFF_W3 + net * W3_BYTES,
+                               smem + OFF_LO + OFF_W3 + net * W3_BYTES, tid);
         for (int i = tid; i < N3 * NACT; i += THREADS) sC[C_WH + net * N3 * NACT + i] = __ldg(p.params + B.wh(net) + i);
         if (tid < NACT) sC[C_BH + net * NACT + tid] = __ldg(p.params + B.bh(net) + tid);
     }
@@ -265,11 +298,27 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
     uint32_t phase = 0;
     constexpr uint32_t B1_LBO = N1 * 16, B2_LBO = N2 * 16;
 
+    {   // the constant A chunk (1, 0, ..., 0) of the bias k-steps: 8 columns of packed float16 per lane, written once
+        uint32_t one[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) one[j] = 0u;
+        one[0] = 0x00003C00u;                                          // (1.0h, 0.0h)
+        if (half == 0) tmem_st16(lane_addr + COL_ONE, one);
+        tmem_st_wait();
+    }
     const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
-    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + g; tile < n_tiles; tile += (int64_t)gridDim.x * GROUPS) {
+    if (g == 1) turn_pass(1);                                          // group 0 takes the first turn
+    // both groups run the same number of rounds (group 0 never has fewer tiles); a group without a tile in the last
+    // round only keeps the turn moving
+    for (int64_t tile0 = (int64_t)blockIdx.x * GROUPS; tile0 < n_tiles; tile0 += (int64_t)gridDim.x * GROUPS) {
+        const int64_t tile = tile0 + g;
+        if (tile >= n_tiles) {
+            for (int k = 0; k < 6; ++k) { turn_wait(g); turn_pass(g); }
+            continue;
+        }
         const int64_t e = tile * ROWS + t;
         const bool live = e < p.n;
-        {   // observation row -> (normalise) -> split float16 -> TMEM columns [224,256)
+        if (half == 0) {   // observation row -> (normalise) -> split float16 -> TMEM columns [224,256)
             float x[K1];
 #pragma unroll
             for (int k = 0; k < K1; ++k) x[k] = 0.f;
@@ -292,6 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
 #pragma unroll
                 for (int k = 0; k < OBS; ++k) x[k] = fminf(fmaxf(x[k], -60000.f), 60000.f);   // float16 range
             }
+            x[OBS] = 1.0f;                                              // multiplies the bias row of W1
             put32<PRECISE>(lane_addr + COL_X, x);
         }
         tmem_st_wait();
@@ -303,9 +353,9 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
 #pragma unroll 1
         for (int net = 0; net < 2; ++net) {
             // ---------------- layer 1: X[128 x 32] . W1^T -> R1[128 columns]
-            if (t == 0) {
+            if (tg == 0) {
                 tc_fence_after();
-                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_X, K1, sbase + OFF_W1 + net * W1_BYTES, sbase + OFF_LO + OFF_W1 + net * W1_BYTES, B1_LBO, N1);
+                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_X, K1, sbase + OFF_W1 + net * W1_BYTES, sbase + OFF_LO + OFF_W1 + net * W1_BYTES, B1_LBO, N1, 0);
                 umma_commit(bar);
             }
             __syncwarp();
@@ -313,19 +363,21 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
             phase ^= 1;
             __syncwarp();
             tc_fence_after();
+            turn_wait(g);
 #pragma unroll 1
-            for (int cb = 0; cb < N1 / 32; ++cb) {
+            for (int cb = half; cb < N1 / 32; cb += 2) {
                 float y[32];
-                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, sC + C_B1 + net * N1 + cb * 32, y);
+                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, y);
                 put32<PRECISE>(lane_addr + COL_R1 + cb * 32, y);        // in place: hi | lo
             }
+            turn_pass(g);
             tmem_st_wait();
             tc_fence_before();
             group_bar(g);
             // ---------------- layer 2: H1[128 x 128] . W2^T -> R2[64 columns]
-            if (t == 0) {
+            if (tg == 0) {
                 tc_fence_after();
-                issue_layer<PRECISE>(tmem + COL_R2, tmem + COL_R1, N1, sbase + OFF_W2 + net * W2_BYTES, sbase + OFF_LO + OFF_W2 + net * W2_BYTES, B2_LBO, N2);
+                issue_layer<PRECISE>(tmem + COL_R2, tmem + COL_R1, N1, sbase + OFF_W2 + net * W2_BYTES, sbase + OFF_LO + OFF_W2 + net * W2_BYTES, B2_LBO, N2, tmem + COL_ONE);
                 umma_commit(bar);
             }
             __syncwarp();
@@ -333,19 +385,21 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
             phase ^= 1;
             __syncwarp();
             tc_fence_after();
-#pragma unroll 1
-            for (int cb = 0; cb < N2 / 32; ++cb) {
+            turn_wait(g);
+            {
+                const int cb = half;
                 float y[32];
-                act32<PRECISE>(lane_addr + COL_R2 + cb * 32, sC + C_B2 + net * N2 + cb * 32, y);
+                act32<PRECISE>(lane_addr + COL_R2 + cb * 32, y);
                 put32<PRECISE>(lane_addr + COL_R2 + cb * 32, y);
             }
+            turn_pass(g);
             tmem_st_wait();
             tc_fence_before();
             group_bar(g);
             // ---------------- layer 3: H2[128 x 64] . W3^T -> R1[first 64 columns], then the float32 head
-            if (t == 0) {
+            if (tg == 0) {
                 tc_fence_after();
-                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_R2, N2, sbase + OFF_W3 + net * W3_BYTES, sbase + OFF_LO + OFF_W3 + net * W3_BYTES, B2_LBO, N3);
+                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_R2, N2, sbase + OFF_W3 + net * W3_BYTES, sbase + OFF_LO + OFF_W3 + net * W3_BYTES, B2_LBO, N3, tmem + COL_ONE);
                 umma_commit(bar);
             }
             __syncwarp();
@@ -355,11 +409,12 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
             tc_fence_after();
             float o[NACT];
 #pragma unroll
-            for (int j = 0; j < NACT; ++j) o[j] = sC[C_BH + net * NACT + j];
-#pragma unroll 1
-            for (int cb = 0; cb < N3 / 32; ++cb) {
+            for (int j = 0; j < NACT; ++j) o[j] = half == 0 ? sC[C_BH + net * NACT + j] : 0.f;
+            turn_wait(g);
+            {
+                const int cb = half;
                 float y[32];
-                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, sC + C_B3 + net * N3 + cb * 32, y);
+                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, y);
                 const float4* wh = reinterpret_cast<const float4*>(sC + C_WH + net * N3 * NACT + cb * 32 * NACT);
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
@@ -370,16 +425,20 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
                     o[3] = fmaf(y[k], w.w, o[3]);
                 }
             }
-            if (net == 0) {
-#pragma unroll
-                for (int j = 0; j < NACT; ++j) mean[j] = o[j];
-            } else {
-                value = o[0];
-            }
+            turn_pass(g);
+            if (half == 1) *reinterpret_cast<float4*>(&s_part[g][t][0]) = make_float4(o[0], o[1], o[2], o[3]);
             tc_fence_before();   // the next MMAs overwrite TMEM columns this thread has just read
             group_bar(g);
+            if (half == 0) {
+                const float4 q = *reinterpret_cast<const float4*>(&s_part[g][t][0]);
+                if (net == 0) {
+                    mean[0] = o[0] + q.x; mean[1] = o[1] + q.y; mean[2] = o[2] + q.z; mean[3] = o[3] + q.w;
+                } else {
+                    value = o[0] + q.x;
+                }
+            }
         }
-        if (live) {
+        if (live && half == 0) {
             const float ls[4] = {sC[C_LS], sC[C_LS + 1], sC[C_LS + 2], sC[C_LS + 3]};
             float4 eps = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.noise) eps = __ldcs(reinterpret_cast<const float4*>(p.noise) + e);

@@ -245,13 +245,49 @@ def run_gpu(args) -> None:
     for i in range(args.warmup):
         one_step(i)
     barrier()
+    # CUDA-graph replay of the step loop (4 steps per graph, so the 4 action / noise buffers rotate exactly as in eager
+    # mode): removes the host launch path (Python -> ctypes -> cudaLaunch, ~5 launches per step) from the critical path
+    unroll = 4 if (args.graph and args.steps % 4 == 0) else 0
+    graph = None
+    if unroll:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(unroll):
+                one_step(i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(unroll):
+                one_step(i)
+        graph.replay()
+        barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    step_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    policy_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     ev0.record()
-    for i in range(args.steps):
+    if graph is not None:
+        for _ in range(args.steps // unroll):
+            graph.replay()
+    else:
+        for i in range(args.steps):
+            one_step(i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = n * world * args.steps / (ms_total / 1e3)
+
+    # ---- per-kernel durations for the roofline: a separate eager pass with CUDA events around each launch (untimed) ----
+    probe = 40
+    step_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(probe)]
+    policy_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(probe)]
+    for i in range(probe):
         if policy is not None:
             if vn is not None:
                 vn.update(env.obs)
@@ -265,17 +301,9 @@ def run_gpu(args) -> None:
             step_events[i][0].record()
             env.step(ring[i & 3])
             step_events[i][1].record()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in step_events)
-    policy_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in policy_events) if policy is not None else None
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = n * world * args.steps / (ms_total / 1e3)
+    torch.cuda.synchronize()
+    step_kernel_ms = statistics.median(a.elapsed_time(b) for a, b in step_events)
+    policy_kernel_ms = statistics.median(a.elapsed_time(b) for a, b in policy_events) if policy is not None else None
 
     # ---- end to end through the SB3-style VecEnv call: pinned host actions in, obs/reward/done out --------
     from rl_aerial_manipulator_b200.vec_env import QuadVecEnv
@@ -344,7 +372,7 @@ def run_gpu(args) -> None:
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": workload_name(args), "envs_per_gpu": n, "envs_total": n * world, "integrator": f"rk4x{args.substeps}",
-                           "vecnormalize": bool(vn is not None),
+                           "vecnormalize": bool(vn is not None), "cuda_graph": bool(graph is not None),
                            "actions": "policy (ppo_model_2300000_steps weights, stochastic, clipped)" if policy else "uniform-random over the action box, 4 pre-generated device buffers",
                            "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
                            "parallelism": f"env-shard x{world}, no data-path collective"},
@@ -369,6 +397,7 @@ def main():
     ap.add_argument("--substeps", type=int, default=1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--vecnorm", type=int, default=1, help="rollout workload: update VecNormalize statistics every step (NCCL all-gather when N>1)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step loop from a CUDA graph (4 steps per graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -141,6 +141,7 @@ class QuadVecEnv(_SB3VecEnv):
         self._flip = 0
         self._h_obs, self._h_reward, self._h_flags = self._h_bufs[0]
         self._pending = False
+        self._transform = None      # optional device-side post-processing of a step (QuadVecNormalize installs one)
         self.h2d_bytes_per_step = n * 4 * 4
         self.d2h_bytes_per_step = n * d * 4 + n * self._h_reward.element_size() + n
 
@@ -161,8 +162,9 @@ class QuadVecEnv(_SB3VecEnv):
         with torch.cuda.stream(self._stream):
             self._d_actions.copy_(self._h_actions, non_blocking=True)
             out = self.sim.step(self._d_actions)
-            self._h_obs.copy_(out.obs, non_blocking=True)
-            self._h_reward.copy_(out.reward, non_blocking=True)
+            obs_t, rew_t = self._transform(out) if self._transform is not None else (out.obs, out.reward)
+            self._h_obs.copy_(obs_t, non_blocking=True)
+            self._h_reward.copy_(rew_t, non_blocking=True)
             self._h_flags.copy_(out.flags, non_blocking=True)
         self._pending = True
 

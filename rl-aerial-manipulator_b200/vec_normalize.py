@@ -69,6 +69,8 @@ class DeviceRunningMeanStd:
         self._scratch = torch.empty(int(self.lib.qs_moments_scratch_len(dim)), dtype=torch.float64, device=self.device)
         self._moments = torch.zeros(1 + 2 * dim, dtype=torch.float64, device=self.device)
         self._gathered = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:   # pre-allocate: update() may run under graph capture
+            self._gathered = torch.empty((dist.get_world_size(group), 1 + 2 * dim), dtype=torch.float64, device=self.device)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -151,18 +153,22 @@ class DeviceVecNormalize:
         if self.training:
             if self.norm_obs:
                 self.obs_rms.update(out.obs)
-            # `returns = returns*gamma + reward; ret_rms.update(returns); returns[dones] = 0` (runs even with norm_reward=False)
-            rc = self.lib.qs_returns_update(C.c_void_p(self.returns.data_ptr()), C.c_void_p(out.reward.data_ptr()),
-                                            int(out.reward.dtype == torch.float64), C.c_void_p(out.flags.data_ptr()), self.gamma,
-                                            self.env.n_envs, C.c_void_p(self._ret_snapshot.data_ptr()), self.obs_rms._stream())
-            self.obs_rms._check(rc, "qs_returns_update")
-            self.ret_rms.update(self._ret_snapshot)
+            self.update_returns(out)
         if self.norm_obs:
             out.obs = self.obs_rms.normalize(out.obs, self.norm_obs_buf, self.epsilon, self.clip_obs)
             out.terminal_obs = self.obs_rms.normalize(out.terminal_obs, self.norm_terminal_obs, self.epsilon, self.clip_obs)
         if self.norm_reward:
             out.reward = torch.clamp(out.reward / torch.sqrt(self.ret_rms.var[0] + self.epsilon), -self.clip_reward, self.clip_reward)
         return out
+
+    def update_returns(self, out) -> None:
+        """`returns = returns*gamma + reward; ret_rms.update(returns); returns[dones] = 0` (VecNormalize.step_wait; SB3 runs
+        it even with norm_reward=False -- the reference's pkl has ret_rms.count = 2031616.0001)."""
+        rc = self.lib.qs_returns_update(C.c_void_p(self.returns.data_ptr()), C.c_void_p(out.reward.data_ptr()),
+                                        int(out.reward.dtype == torch.float64), C.c_void_p(out.flags.data_ptr()), self.gamma,
+                                        self.env.n_envs, C.c_void_p(self._ret_snapshot.data_ptr()), self.obs_rms._stream())
+        self.obs_rms._check(rc, "qs_returns_update")
+        self.ret_rms.update(self._ret_snapshot)
 
     def state_dict(self) -> dict:
         """Field names of stable_baselines3's pickled VecNormalize (see tests/golden/vecnorm_v1.npz)."""

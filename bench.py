@@ -31,6 +31,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 ALGO_BYTES = {("v2", "f32"): 269, ("v2", "f64"): 425, ("v1", "f32"): 249}
@@ -40,69 +49,93 @@ POLICY_FLOPS = 60032                                                         # a
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference step on the host cores
 # --------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    seed, n_env, seconds = args
+_CPU = {}
+
+
+def _cpu_init(n_env):
+    """Pool initializer: one v2 VecOracle per worker process (float64, SciPy LSODA like quadcopter.py:113, auto-reset)."""
     os.environ["OMP_NUM_THREADS"] = "1"
     import numpy as np
 
     from oracle import quad_oracle as qo
 
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(os.getpid())
     vec = qo.VecOracle("v2", n_env, lambda ids, eps: rng.random((len(ids), qo.N_UNIFORMS)), integrator="lsoda")
     vec.reset()
-    lo, hi = np.array([0, -1, -1, -1.0]), np.array([2, 1, 1, 1.0])
-    done_steps = 0
-    t0 = time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
-        a = (lo + (hi - lo) * rng.random((n_env, 4))).astype(np.float32)
+    _CPU.update(np=np, rng=rng, vec=vec, n=n_env, lo=np.array([0, -1, -1, -1.0]), hi=np.array([2, 1, 1, 1.0]))
+
+
+def _cpu_chunk(seconds):
+    """Step this worker's envs with uniform-random float32 actions for `seconds`; returns (env-steps, elapsed)."""
+    np, rng, vec, n = _CPU["np"], _CPU["rng"], _CPU["vec"], _CPU["n"]
+    done, t0 = 0, time.perf_counter()
+    while True:
+        a = (_CPU["lo"] + (_CPU["hi"] - _CPU["lo"]) * rng.random((n, 4))).astype(np.float32)
         with np.errstate(all="ignore"):
             vec.step(a)
-        done_steps += n_env
-    return done_steps, time.perf_counter() - t0
+        done += n
+        if time.perf_counter() - t0 >= seconds:
+            return done, time.perf_counter() - t0
 
 
-def cpu_baseline(seconds: float = 12.0, n_env: int = 8, procs: int | None = None) -> dict:
-    """v2 step + auto-reset, uniform-random float32 actions, scipy LSODA like the reference; one process per core."""
-    import multiprocessing as mp
+class CpuArm:
+    """The CPU arm: oracle port of the reference step, one process per host core (the SubprocVecEnv-style layout)."""
 
-    cores = procs or (os.cpu_count() or 1)
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(1000 + i, n_env, seconds) for i in range(cores)])
-    wall = time.perf_counter() - t0
-    total = sum(r[0] for r in res)
-    longest = max(r[1] for r in res)
-    return {"value": total / longest, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{total} env-steps of v2 (float64, scipy LSODA like quadcopter.py:113, auto-reset, uniform-random "
-                      f"float32 actions) by oracle/quad_oracle.py, {cores} processes x {n_env} envs for {seconds:.0f} s "
-                      f"(wall {wall:.1f} s)"}
+    def __init__(self, n_env: int = 8, procs: int | None = None):
+        import multiprocessing as mp
+
+        self.cores = procs or (os.cpu_count() or 1)
+        self.n_env = n_env
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(n_env,))
+
+    def sample(self, seconds: float):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_chunk, [seconds] * self.cores, chunksize=1)
+        wall = time.perf_counter() - t0
+        return sum(r[0] for r in res), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, total, wall, what):
+        return (f"{total} env-steps of v2 (float64, scipy LSODA like quadcopter.py:113, auto-reset, uniform-random float32 actions) by "
+                f"oracle/quad_oracle.py, {self.cores} processes x {self.n_env} envs, {what} (wall {wall:.1f} s)")
+
+
+def cpu_baseline(seconds: float = 12.0) -> dict:
+    arm = CpuArm()
+    arm.sample(0.5)
+    total, wall = arm.sample(seconds)
+    arm.close()
+    return {"value": total / wall, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.describe(total, wall, f"one {seconds:.0f} s sample")}
 
 
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = max(2.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
-    vals = []
+    # each "step" is one bounded sample on all host cores; the whole K + W run is sized to ~75 s
+    per_step = max(0.02, min(10.0, 75.0 / max(1, args.steps + args.warmup)))
+    arm = CpuArm()
     for _ in range(args.warmup):
-        cpu_baseline(seconds=per_step)
-    t0 = time.perf_counter()
-    base = None
+        arm.sample(per_step)
+    total, t0 = 0, time.perf_counter()
     for _ in range(args.steps):
-        base = cpu_baseline(seconds=per_step)
-        vals.append(base["value"])
-    ms = (time.perf_counter() - t0) * 1e3 / max(1, args.steps)
-    value = statistics.mean(vals)
-    base["value"] = value
+        total += arm.sample(per_step)[0]
+    wall = time.perf_counter() - t0
+    arm.close()
+    value = total / wall
+    base = {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
+            "sample": arm.describe(total, wall, f"{args.steps} samples of {per_step * 1e3:.0f} ms")}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "note": "CPU oracle port of the reference step (the reference tree is not on the GPU box); "
                        "each step = one bounded sample on all host cores"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -380,9 +413,13 @@ def run_gpu(args) -> None:
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                         "api": "QuadVecEnv.step(actions: np.ndarray) -> obs, rewards, dones, infos (pinned staging, info_mode=lazy)"},
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # no destroy_process_group(): tearing down a communicator that a captured CUDA graph still references can block;
+        # every rank has passed the final all_reduce, so leave without running the destructors
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -406,6 +443,11 @@ def main():
     if args.cpu_baseline_only:
         print(json.dumps(cpu_baseline()), flush=True)
         return
+    # rank 0 must print exactly ONE line on stdout: park the real stdout and send everything else (NCCL's version banner,
+    # library chatter) to stderr
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
         return

@@ -129,8 +129,8 @@ def test_quad_vecnormalize_wrapper_vs_oracle(tmp_path):
     np.testing.assert_allclose(obs, ref.reset(vn.get_original_obs()), rtol=3e-5, atol=3e-5)
     rng = np.random.default_rng(0)
     n_done = 0
-    for t in range(120):
-        a = np.stack([rng.uniform(0, 0.7, n), *rng.uniform(-1, 1, (3, n))], 1).astype(np.float32)
+    for t in range(200):
+        a = np.stack([rng.uniform(0, 0.4, n), *rng.uniform(-1, 1, (3, n))], 1).astype(np.float32)
         obs, rew, dones, infos = vn.step(a)
         want = ref.step(vn.get_original_obs(), vn.get_original_reward(), dones)
         np.testing.assert_allclose(obs, want, rtol=3e-5, atol=3e-5)

@@ -249,7 +249,8 @@ def run_gpu(args) -> None:
             # VecNormalize(norm_obs=True): moments of this rank's shard -> all-gather of 2D+1 doubles over NCCL (N>1)
             # -> Chan merge on device -> normalisation fused into the policy kernel's obs load
             vn = DeviceRunningMeanStd(env.obs_dim, dev)
-            launches_per_step = 5
+            vn.attach(env)                                   # the step kernel reduces the obs it returns: no separate read pass
+            launches_per_step = 4                            # env step + moments_final + merge + policy forward
     # uniform-random actions over the action box, pre-generated ring (step workload) / sampling noise (rollout)
     g = torch.Generator(device=dev).manual_seed(args.seed + rank)
     lo = torch.tensor([0.0, -1, -1, -1], device=dev)
@@ -260,7 +261,7 @@ def run_gpu(args) -> None:
 
     def policy_step(i):
         if vn is not None:
-            vn.update(env.obs)
+            vn.update_from_moments()                         # all-gather over ranks (N > 1) + Chan merge on device
         policy.forward(env.obs, noise[i & 3], norm_stats=vn.stats if vn is not None else None)   # -> policy.actions_clipped
 
     def one_step(i):
@@ -323,7 +324,7 @@ def run_gpu(args) -> None:
     for i in range(probe):
         if policy is not None:
             if vn is not None:
-                vn.update(env.obs)
+                vn.update_from_moments()
             policy_events[i][0].record()
             policy.forward(env.obs, noise[i & 3], norm_stats=vn.stats if vn is not None else None)
             policy_events[i][1].record()

@@ -135,6 +135,14 @@ int qs_reset(qs_handle* h, const uint8_t* env_mask, float* obs_out, void* stream
 int qs_step(qs_handle* h, const float* actions, float* obs_out, void* reward_out, uint8_t* flags_out,
             float* terminal_obs_out, void* ep_return_out, int32_t* ep_len_out, void* stream);
 
+/*
+ * Fused VecNormalize moments: after this call every qs_step also leaves (n, mean[D], M2[D]) of the observations it
+ * returned (f64[1+2D], device, caller-owned) in `moments_out` -- what RunningMeanStd.update(obs) needs -- computed inside the
+ * step kernel from the obs tile it already holds.  shift_stats: VecNormalize stats f64[1+2D] whose mean is used as the
+ * summation offset (conditioning), or NULL.  moments_out == NULL switches the feature off.
+ */
+int qs_step_moments(qs_handle* h, double* moments_out, const double* shift_stats);
+
 int qs_get_state(qs_handle* h, const qs_state_view* out, void* stream);
 int qs_set_state(qs_handle* h, const qs_state_view* in, void* stream);
 

@@ -103,12 +103,13 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.qs_state_bytes_per_env.restype = i64
     lib.qs_reset.argtypes = [vp, vp, vp, vp]
     lib.qs_step.argtypes = [vp] + [vp] * 7 + [vp]
+    lib.qs_step_moments.argtypes = [vp, vp, vp]
     lib.qs_get_state.argtypes = [vp, C.POINTER(QsStateView), vp]
     lib.qs_set_state.argtypes = [vp, C.POINTER(QsStateView), vp]
     lib.qs_reset_uniforms.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.qs_lsoda_stats.argtypes = [vp, vp, vp, vp]
     for name in ("qs_create", "qs_destroy", "qs_obs_dim", "qs_reset", "qs_step", "qs_get_state", "qs_set_state",
-                 "qs_reset_uniforms", "qs_lsoda_stats"):
+                 "qs_reset_uniforms", "qs_lsoda_stats", "qs_step_moments"):
         getattr(lib, name).restype = C.c_int
     if lib.qs_abi_version() != QS_ABI_VERSION:
         raise RuntimeError(f"libquadsim ABI {lib.qs_abi_version()} != binding ABI {QS_ABI_VERSION}; rebuild")

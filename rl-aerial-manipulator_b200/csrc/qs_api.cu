@@ -168,6 +168,9 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
         return QS_ENOMEM;
     }
     cudaMemset(h->pool, 0, bytes);
+    h->mom_scratch = nullptr;
+    h->mom_out = nullptr;
+    h->mom_stats = nullptr;
     h->ls_tables = nullptr;
     h->ls_counters = nullptr;
     h->ls_steps = nullptr;
@@ -192,6 +195,7 @@ int qs_destroy(qs_handle* h) {
     if (!h) return QS_OK;
     cudaSetDevice(h->cfg.device);
     if (h->pool) cudaFree(h->pool);
+    if (h->mom_scratch) cudaFree(h->mom_scratch);
     if (h->ls_tables) cudaFree(h->ls_tables);
     if (h->ls_counters) cudaFree(h->ls_counters);
     if (h->ls_steps) cudaFree(h->ls_steps);
@@ -233,6 +237,19 @@ int qs_step(qs_handle* h, const float* actions, float* obs_out, void* reward_out
     else
         rc = launch_step_lsoda(h, actions, obs_out, (double*)reward_out, flags_out, terminal_obs_out, (double*)ep_return_out, ep_len_out, (cudaStream_t)stream);
     return rc;
+}
+
+int qs_step_moments(qs_handle* h, double* moments_out, const double* shift_stats) {
+    if (!h) { set_error(nullptr, "qs_step_moments: null handle"); return QS_EINVAL; }
+    QS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (moments_out && !h->mom_scratch) {
+        const int d = h->cfg.env_version == 2 ? 20 : 17;
+        // upper bound of any step grid: 16 resident CTAs of 128 threads per SM
+        QS_CUDA(h, cudaMalloc(&h->mom_scratch, sizeof(double) * 2 * d * (size_t)h->num_sms * 16));
+    }
+    h->mom_out = moments_out;
+    h->mom_stats = moments_out ? shift_stats : nullptr;
+    return QS_OK;
 }
 
 int qs_get_state(qs_handle* h, const qs_state_view* out, void* stream) {

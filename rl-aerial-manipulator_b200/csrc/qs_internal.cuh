@@ -9,6 +9,9 @@ struct qs_handle {
     void* pool;
     size_t pool_bytes;
     int64_t bytes_per_env;
+    double* mom_scratch;      // fused obs moments: per-CTA partials [grid][2*obs_dim]; null = off
+    double* mom_out;          // caller-owned (n, mean[D], M2[D]) triplet
+    const double* mom_stats;  // caller-owned VecNormalize stats used as the shift (or null)
     qs::LsodaTables* ls_tables;
     int32_t* ls_counters;
     double* ls_steps;
@@ -19,6 +22,9 @@ struct qs_handle {
 
 namespace qs {
 void set_error(qs_handle* h, const char* fmt, ...);
+
+// (n, mean, M2) from the per-CTA partials a step kernel launched with `blocks` CTAs left in h->mom_scratch (qs_vecnorm.cu)
+int launch_moments_final(qs_handle* h, unsigned blocks, cudaStream_t st);
 
 int launch_step_f32(qs_handle* h, const float* actions, float* obs, float* reward, uint8_t* flags, float* term_obs,
                     float* ep_ret, int32_t* ep_len, cudaStream_t st);
@@ -34,6 +40,9 @@ inline StepParams<Real> base_params(const qs_handle* h) {
     StepParams<Real> p;
     p.pool = h->pool;
     p.n = c.n_envs;
+    p.mom_partial = h->mom_out ? h->mom_scratch : nullptr;
+    p.mom_stats = h->mom_stats;
+    p.mom_prev = h->mom_out;
     p.ls_tables = h->ls_tables;
     p.ls_counters = h->ls_counters;
     p.ls_steps = h->ls_steps;

@@ -9,6 +9,9 @@
 //   -> auto-reset with Philox draws for done envs        [DummyVecEnv.step_wait + reset()]
 //   -> store state planes; obs rows leave through a per-warp shared-memory transpose so the
 //      [n, obs_dim] row-major output is written with full 128-bit coalesced stores.
+//   -> optionally, VecNormalize's batch moments of the returned observations: lane c of each warp adds column c of
+//      the warp's shared-memory obs tile in float64 (conflict-free: row stride OBS+1), CTA partials are combined
+//      in shared memory and written once per CTA -- the separate 34 us read pass over the obs disappears.
 #pragma once
 #include "qs_pool.cuh"
 #include "qs_lsoda.cuh"
@@ -29,6 +32,10 @@ struct StepParams {
     Real* ep_ret_out;           // [n] or null
     int32_t* ep_len_out;        // [n] or null
     const LsodaTables* ls_tables; // device copy of the method coefficients (LSODA mode)
+    double* mom_partial;        // [gridDim.x][2*OBS] per-CTA column sums of (obs - shift), (obs - shift)^2, or null
+    const double* mom_stats;    // VecNormalize stats (count, mean[OBS], var[OBS]) or null
+    const double* mom_prev;     // the previous step's triplet (n, mean, M2): its mean is the summation offset G when n > 0,
+                                // else the running mean of mom_stats, else 0 (moments_final_kernel applies the same rule)
     int32_t* ls_counters;       // [n,4] or null (LSODA diagnostics)
     double* ls_steps;           // [n,2] or null
     int substeps, obs_scaled, scale_f32, auto_reset;
@@ -71,11 +78,18 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, const f
     }
 }
 
-template <typename Real, int VER, int INTEG>
+template <typename Real, int VER, int INTEG, bool MOMENTS = false>
 __global__ void __launch_bounds__(STEP_BLOCK, StepOcc<Real, INTEG>::MINB) env_step_kernel(const StepParams<Real> p) {
     constexpr int OBS = EnvTraits<VER>::OBS;
     __shared__ float s_tile[STEP_BLOCK / 32][32 * (OBS + 1)];
+    __shared__ double s_mom[MOMENTS ? STEP_BLOCK / 32 : 1][2 * OBS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double m1 = 0.0, m2 = 0.0;                       // lane c < OBS: running sums of column c over this warp's tiles
+    double G = 0.0;
+    if (MOMENTS && lane < OBS) {
+        if (p.mom_prev && p.mom_prev[0] > 0.0) G = p.mom_prev[1 + lane];
+        else if (p.mom_stats) G = p.mom_stats[1 + lane];
+    }
     const int64_t warps_total = (int64_t)gridDim.x * (STEP_BLOCK / 32);
     const int64_t n_warp_tiles = (p.n + 31) / 32;
     float* tile = s_tile[warp];
@@ -136,8 +150,40 @@ __global__ void __launch_bounds__(STEP_BLOCK, StepOcc<Real, INTEG>::MINB) env_st
         }
         __syncwarp();
         const int64_t rem = p.n - e0;
-        warp_store_rows<OBS>(p.obs_out + e0 * OBS, tile, lane, rem < 32 ? (int)rem : 32);
+        const int rows = rem < 32 ? (int)rem : 32;
+        warp_store_rows<OBS>(p.obs_out + e0 * OBS, tile, lane, rows);
+        if (MOMENTS && lane < OBS) {
+            // float32 sums over 8 rows of (obs - L), L = the tile's first row (deviations ~ one sigma: always well conditioned),
+            // re-centred to the global offset G in float64 once per tile:  sum(x-G) = sum(x-L) + k(L-G), and the square likewise
+            const float L = tile[lane];
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int r = r0; r < r0 + 8; ++r) {
+                    const float v = r < rows ? tile[r * (OBS + 1) + lane] - L : 0.f;
+                    a1 += v;
+                    a2 = fmaf(v, v, a2);
+                }
+                t1 += (double)a1;
+                t2 += (double)a2;
+            }
+            const double dl = (double)L - G;
+            m1 += t1 + (double)rows * dl;
+            m2 += t2 + 2.0 * dl * t1 + (double)rows * dl * dl;
+        }
         __syncwarp();
+    }
+    if (MOMENTS) {
+        if (lane < OBS) { s_mom[warp][lane] = m1; s_mom[warp][OBS + lane] = m2; }
+        __syncthreads();
+        if (threadIdx.x < 2 * OBS) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < STEP_BLOCK / 32; ++w) a += s_mom[w][threadIdx.x];
+            p.mom_partial[(int64_t)blockIdx.x * 2 * OBS + threadIdx.x] = a;
+        }
     }
 }
 

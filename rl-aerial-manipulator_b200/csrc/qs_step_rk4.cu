@@ -17,18 +17,34 @@ static int launch_rk4(qs_handle* h, const float* actions, float* obs, Real* rewa
     p.ep_len_out = ep_len;
     p.ls_counters = nullptr;
     p.ls_steps = nullptr;
+    unsigned grid = 0;
     if (h->cfg.env_version == 2) {
-        auto k = env_step_kernel<Real, ENV_V2, INTEG_RK4>;
-        k<<<step_grid(h, k, STEP_BLOCK), STEP_BLOCK, 0, st>>>(p);
+        if (p.mom_partial) {
+            auto k = env_step_kernel<Real, ENV_V2, INTEG_RK4, true>;
+            grid = step_grid(h, k, STEP_BLOCK);
+            k<<<grid, STEP_BLOCK, 0, st>>>(p);
+        } else {
+            auto k = env_step_kernel<Real, ENV_V2, INTEG_RK4, false>;
+            grid = step_grid(h, k, STEP_BLOCK);
+            k<<<grid, STEP_BLOCK, 0, st>>>(p);
+        }
     } else {
-        auto k = env_step_kernel<Real, ENV_V1, INTEG_RK4>;
-        k<<<step_grid(h, k, STEP_BLOCK), STEP_BLOCK, 0, st>>>(p);
+        if (p.mom_partial) {
+            auto k = env_step_kernel<Real, ENV_V1, INTEG_RK4, true>;
+            grid = step_grid(h, k, STEP_BLOCK);
+            k<<<grid, STEP_BLOCK, 0, st>>>(p);
+        } else {
+            auto k = env_step_kernel<Real, ENV_V1, INTEG_RK4, false>;
+            grid = step_grid(h, k, STEP_BLOCK);
+            k<<<grid, STEP_BLOCK, 0, st>>>(p);
+        }
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error(h, "env_step_kernel launch failed: %s", cudaGetErrorString(err));
         return QS_ECUDA;
     }
+    if (p.mom_partial) return launch_moments_final(h, grid, st);
     return QS_OK;
 }
 

@@ -21,6 +21,7 @@
 //   apply            normalise + clip, float4 vectorised when rows are 16-byte aligned
 //   returns_update   the discounted-return recursion feeding ret_rms
 #include "../../include/quadsim.h"
+#include "qs_internal.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -63,10 +64,17 @@ __global__ void moments_partial_kernel(const float* __restrict__ x, int64_t n, i
 // Fixed-order sum of the CTA partials: 1024 threads = 16 slices x 64 columns (2d <= 64); each slice adds its share of the
 // partials in block order, then the 16 slice sums are added in slice order -> deterministic, ~2 us instead of a 100 us
 // single-thread chain.
-__global__ void __launch_bounds__(1024) moments_final_kernel(const float* __restrict__ x, const double* __restrict__ partial, int blocks,
-                                                             int64_t n, int d, double* __restrict__ out /*[1+2d]*/) {
+// shift: per-column offset the partial sums were taken around -- row 0 of x (qs_batch_moments) or the running mean
+// stats[1..d] (fused moments of the env-step kernel; x == nullptr), or zero when both are null.
+__global__ void __launch_bounds__(1024) moments_final_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                             const double* __restrict__ partial, int blocks, int64_t n, int d,
+                                                             double* __restrict__ out /*[1+2d]*/) {
     __shared__ double s[16][64];
     const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    // fused path (x == nullptr): same offset rule as env_step_kernel -- the previous triplet's mean if it has one.  Read it
+    // before the barrier below; the triplet is overwritten after it.
+    double shift = 0.0;
+    if (threadIdx.x < d) shift = x ? (double)x[threadIdx.x] : (out[0] > 0.0 ? out[1 + threadIdx.x] : (stats ? stats[1 + threadIdx.x] : 0.0));
     double acc = 0.0;
     if (col < 2 * d)
         for (int b = slice; b < blocks; b += 16) acc += partial[(int64_t)b * 2 * d + col];
@@ -76,7 +84,6 @@ __global__ void __launch_bounds__(1024) moments_final_kernel(const float* __rest
         const int c = threadIdx.x;
         double s1 = 0.0, s2 = 0.0;
         for (int k = 0; k < 16; ++k) { s1 += s[k][c]; s2 += s[k][d + c]; }
-        const double shift = (double)x[c];
         const double cnt = (double)n;
         out[1 + c] = shift + s1 / cnt;               // batch mean
         out[1 + d + c] = s2 - s1 * s1 / cnt;         // batch M2 = sum (x - mean)^2
@@ -159,6 +166,17 @@ static int vn_check(cudaError_t err, const char* what) {
     return QS_OK;
 }
 
+int launch_moments_final(qs_handle* h, unsigned blocks, cudaStream_t st) {
+    const int d = h->cfg.env_version == 2 ? 20 : 17;
+    moments_final_kernel<<<1, 1024, 0, st>>>(nullptr, h->mom_stats, h->mom_scratch, (int)blocks, h->cfg.n_envs, d, h->mom_out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error(h, "moments_final_kernel launch failed: %s", cudaGetErrorString(err));
+        return QS_ECUDA;
+    }
+    return QS_OK;
+}
+
 }  // namespace qs
 
 using namespace qs;
@@ -180,7 +198,7 @@ int qs_batch_moments(const float* x, int64_t n, int d, double* moments_out, doub
     if (blocks > MOM_MAX_BLOCKS) blocks = MOM_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
     moments_partial_kernel<<<(unsigned)blocks, bd, 2 * bd * sizeof(double), (cudaStream_t)stream>>>(x, n, d, scratch);
-    moments_final_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, scratch, (int)blocks, n, d, moments_out);
+    moments_final_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, nullptr, scratch, (int)blocks, n, d, moments_out);
     return vn_check(cudaGetLastError(), "qs_batch_moments");
 }
 

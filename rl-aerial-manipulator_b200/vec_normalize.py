@@ -100,7 +100,19 @@ class DeviceRunningMeanStd:
 
     def update(self, x: torch.Tensor) -> None:
         """RunningMeanStd.update(x) for the batch sharded over all ranks of `group` (or this GPU alone)."""
-        m = self.batch_moments(x)
+        self.update_from_moments(self.batch_moments(x))
+
+    def attach(self, env) -> None:
+        """Let `env`'s step kernel produce the batch moments of the observations it returns (no separate read pass):
+        after every env.step(), call update_from_moments()."""
+        self.batch_moments(env.obs)                     # seeds the summation offset with the current observations' mean
+        env.fuse_obs_moments(self._moments, self.stats)
+
+    def update_from_moments(self, m: torch.Tensor | None = None) -> None:
+        """Merge a batch triplet (n, mean, M2) -- by default `self._moments`, e.g. filled by the env-step kernel
+        (BatchedQuadEnv.fuse_obs_moments) -- into the running statistics, all-gathering over the ranks first."""
+        if m is None:
+            m = self._moments
         k = 1
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             k = dist.get_world_size(self.group)

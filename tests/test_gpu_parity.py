@@ -398,3 +398,57 @@ def test_error_paths():
     with pytest.raises(ValueError):
         env.step(torch.zeros((8, 3), device="cuda"))
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# (d) the SB3 VecEnv surface (NumPy in/out, infos) against the oracle's DummyVecEnv/Monitor restatement
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,info_mode", [("v2", "dict"), ("v1", "lazy")])
+def test_quad_vec_env_surface_vs_oracle(variant, info_mode):
+    from rl_aerial_manipulator_b200.vec_env import QuadVecEnv
+    n, steps = 32, 260
+    venv = QuadVecEnv(n, env_version=VERS[variant], precision="f64", integrator="lsoda", seed=8, info_mode=info_mode)
+    assert venv.num_envs == n and venv.observation_space.shape == (20 if variant == "v2" else 17,)
+    np.testing.assert_array_equal(venv.action_space.low, [0, -1, -1, -1])
+    np.testing.assert_array_equal(venv.action_space.high, [2, 1, 1, 1])
+
+    def uniforms(ids, eps):
+        return t2n(venv.sim.reset_uniforms(torch.as_tensor(ids, dtype=torch.int64), torch.as_tensor(eps, dtype=torch.int32)))
+
+    vec = qo.VecOracle(variant, n, uniforms, integrator="lsoda", max_wp=3)
+    obs = venv.reset()
+    assert obs.dtype == np.float32 and obs.shape == (n, venv.sim.obs_dim)
+    np.testing.assert_array_equal(obs, vec.reset())
+    rng = np.random.default_rng(5)
+    seen = {"crashed": 0, "episode": 0, "trunc_key": 0}
+    for t in range(steps):
+        a = np.stack([rng.uniform(0, 0.3, n), *rng.uniform(-1, 1, (3, n))], 1).astype(np.float32)
+        venv.step_async(a)
+        obs, rew, dones, infos = venv.step_wait()
+        with np.errstate(all="ignore"):
+            obs_o, rew_o, done_o, ex = vec.step(a)
+        assert rew.dtype == np.float32 and dones.dtype == np.bool_ and len(infos) == n
+        np.testing.assert_array_equal(dones, done_o)
+        np.testing.assert_allclose(obs, obs_o, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(rew, rew_o.astype(np.float32), rtol=1e-6, atol=1e-5)
+        for i in range(n):
+            info = infos[i]
+            if not dones[i]:
+                assert "terminal_observation" not in info and "episode" not in info
+                continue
+            # DummyVecEnv: terminal_observation + TimeLimit.truncated; Monitor: episode r / l
+            np.testing.assert_allclose(info["terminal_observation"], ex["terminal_obs"][i], rtol=0, atol=1e-6)
+            assert info["TimeLimit.truncated"] == bool(ex["truncated"][i] and not ex["terminated"][i])
+            assert info["episode"]["l"] == ex["ep_len"][i] and abs(info["episode"]["r"] - ex["ep_return"][i]) < 1e-4
+            bits = int(ex["info"][i])
+            assert info.get("crashed", False) == bool(bits & qo.INFO_CRASHED)
+            assert info.get("out_of_bounds", False) == bool(bits & qo.INFO_OOB)
+            if bits & (qo.INFO_CRASHED | qo.INFO_OOB):
+                assert info["success"] is False
+            seen["crashed"] += bool(bits & qo.INFO_CRASHED)
+            seen["episode"] += 1
+    assert seen["episode"] >= n and seen["crashed"] >= n // 2
+    st = venv.get_attr("waypoint_list", [0, 1])
+    assert len(st) == 2 and st[0][0].shape == (3,)
+    assert venv.env_is_wrapped(object) == [False] * n and venv.seed() == [8] * n
+    venv.close()

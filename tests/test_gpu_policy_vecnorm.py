@@ -168,3 +168,40 @@ def test_vecnormalize_pkl_layout_roundtrip(golden_dir):
     want = np.clip((raw - z["obs_mean"]) / np.sqrt(z["obs_var"] + 1e-8), -10, 10)
     np.testing.assert_allclose(t2n(obs), want, rtol=2e-5, atol=2e-5)
     assert float(vn.obs_rms.count) == 2031632.0001     # training=False: statistics frozen
+
+
+@pytest.mark.parametrize("variant,precision,n", [("v2", "f32", 1 << 18), ("v2", "f64", 4099), ("v1", "f32", 33), ("v1", "f64", 70001)])
+def test_fused_obs_moments_in_step_kernel(variant, precision, n):
+    """qs_step_moments: the step kernel's own reduction of the observations it returns == qs_batch_moments(obs) == NumPy."""
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd
+    ver = 2 if variant == "v2" else 1
+    env = BatchedQuadEnv(n, env_version=ver, precision=precision, seed=6)
+    d = env.obs_dim
+    fused = DeviceRunningMeanStd(d, "cuda")
+    plain = DeviceRunningMeanStd(d, "cuda")
+    env.reset()
+    fused.attach(env)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for t in range(30):
+        a = torch.rand((n, 4), device="cuda", generator=g) * torch.tensor([0.6, 2, 2, 2], device="cuda") - torch.tensor([0, 1, 1, 1.0], device="cuda")
+        out = env.step(a.float())
+        m_f = t2n(fused._moments).copy()
+        m_p = t2n(plain.batch_moments(out.obs)).copy()
+        x = t2n(out.obs).astype(np.float64)
+        assert m_f[0] == n
+        # the fused path adds 8 rows at a time in float32 around the running mean (SB3 itself takes the whole batch mean in
+        # float32): 1e-6 of a standard deviation on the mean, 2e-6 relative on M2
+        sd = x.std(0) + 1e-12
+        assert np.all(np.abs(m_f[1:1 + d] - x.mean(0)) <= 1e-6 * sd + 1e-9)
+        np.testing.assert_allclose(m_f[1 + d:], x.var(0) * n, rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(m_p[1:1 + d], x.mean(0), rtol=1e-12, atol=1e-12)
+        fused.update_from_moments()
+        plain.update(out.obs)
+    np.testing.assert_allclose(t2n(fused.stats)[1:1 + d], t2n(plain.stats)[1:1 + d], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(t2n(fused.stats)[1 + d:], t2n(plain.stats)[1 + d:], rtol=3e-6, atol=1e-9)
+    env.fuse_obs_moments(None)
+    before = t2n(fused._moments).copy()
+    env.step(a.float())
+    np.testing.assert_array_equal(t2n(fused._moments), before)       # switched off: untouched
+    env.close()

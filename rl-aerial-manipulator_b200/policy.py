@@ -136,8 +136,11 @@ class MlpPolicyKernel:
                           torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device),
                           torch.Generator(device=self.device).manual_seed(0))
         h_obs, h_act, d_obs, gen = self._host
-        h_obs.numpy()[...] = obs_np
-        d_obs.copy_(h_obs, non_blocking=True)
+        src = torch.from_numpy(np.ascontiguousarray(obs_np, dtype=np.float32))
+        if not src.is_pinned():            # QuadVecEnv returns views of pinned buffers: no host memcpy then
+            h_obs.numpy()[...] = obs_np
+            src = h_obs
+        d_obs.copy_(src, non_blocking=True)
         noise = torch.randn((n, NACT), device=self.device, generator=gen) if stochastic else None
         self.forward(d_obs, noise, norm_stats=norm_stats)
         h_act.copy_(self.actions_clipped, non_blocking=True)

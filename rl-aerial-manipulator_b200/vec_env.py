@@ -155,12 +155,15 @@ class QuadVecEnv(_SB3VecEnv):
         return self._h_obs.numpy().copy()
 
     def step_async(self, actions: np.ndarray) -> None:
-        a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
-        self._h_actions.numpy()[...] = a
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
+        src = torch.from_numpy(a)
+        if not src.is_pinned():            # stage through pinned memory unless the caller already handed us a pinned array
+            self._h_actions.numpy()[...] = a
+            src = self._h_actions
         self._flip ^= 1
         self._h_obs, self._h_reward, self._h_flags = self._h_bufs[self._flip]
         with torch.cuda.stream(self._stream):
-            self._d_actions.copy_(self._h_actions, non_blocking=True)
+            self._d_actions.copy_(src, non_blocking=True)
             out = self.sim.step(self._d_actions)
             obs_t, rew_t = self._transform(out) if self._transform is not None else (out.obs, out.reward)
             self._h_obs.copy_(obs_t, non_blocking=True)

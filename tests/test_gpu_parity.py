@@ -452,3 +452,60 @@ def test_quad_vec_env_surface_vs_oracle(variant, info_mode):
     assert len(st) == 2 and st[0][0].shape == (3,)
     assert venv.env_is_wrapped(object) == [False] * n and venv.seed() == [8] * n
     venv.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# (e) BASELINE.json configs[0] / configs[1]: the reference's own CPU-runnable cases, on the GPU path
+# ------------------------------------------------------------------------------------------------------
+def test_config0_v1_hover_10k_steps():
+    """configs[0]: v1 rl_env_scaledObs, one env, 10,000 steps of the fixed hover action float32 [1,0,0,0] with auto-reset.
+    The reference truncates on the 1,201st step of an episode, so 10,000 steps contain exactly 8 resets (SURVEY appendix A);
+    hovering keeps the vehicle within millimetres of its start."""
+    env = make_env(1, "v1", precision="f64", integrator="lsoda", seed=0)
+    obs0 = env.reset().clone()
+    a = torch.tensor([[1.0, 0, 0, 0]], device="cuda")
+    dones, truncs, terms = 0, 0, 0
+    lens = []
+    for t in range(10000):
+        out = env.step(a)
+        f = int(out.flags[0])
+        if f & 3:
+            dones += 1
+            truncs += bool(f & 2)
+            terms += bool(f & 1)
+            lens.append(int(out.ep_len[0]))
+    assert dones == 8 and truncs == 8 and terms == 0 and lens == [1201] * 8
+    st = env.get_state(["current_step", "episode", "y"])
+    assert int(st["episode"][0]) == 8 and int(st["current_step"][0]) == 10000 - 8 * 1201
+    # F = fl32(fl32(1*fl32(0.18))*fl32(9.81)) = 1.7658001 N vs m*g = 1.7658 N: the hover drifts by < 1 mm per episode
+    assert abs(float(st["y"][0, 5])) < 1e-3
+    env.close()
+
+
+@pytest.mark.parametrize("precision,integrator", [("f64", "lsoda"), ("f32", "rk4")])
+def test_config1_shipped_v1_policy_flies_the_course(golden_dir, precision, integrator):
+    """configs[1]-style closed loop: the reference's shipped v1 policy (waypoint_controller_scaledObs_4M.zip, deterministic
+    actions, SB3-style clipping) drives 512 GPU envs.  On the reference env it reaches every waypoint (SURVEY section 4:
+    6/6 episodes, 252-508 steps, return 2362-5221); the GPU env must give the same picture."""
+    from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+    n = 512
+    env = make_env(n, "v1", precision=precision, integrator=integrator, seed=3)
+    pol = MlpPolicyKernel.from_npz(os.path.join(golden_dir, "policy_v1.npz"), device="cuda", impl="fp32")
+    obs = env.reset()
+    n_success, n_other, lens, rets = 0, 0, [], []
+    for t in range(700):
+        pol.forward(obs)                               # deterministic: the mean action
+        out = env.step(pol.actions_clipped)
+        obs = out.obs
+        flags = t2n(out.flags)
+        d = (flags & 3) != 0
+        if d.any():
+            succ = d & ((flags & 4) != 0)
+            n_success += int(succ.sum())
+            n_other += int((d & ~succ).sum())
+            lens += t2n(out.ep_len)[succ].tolist()
+            rets += t2n(out.ep_return)[succ].tolist()
+    assert n_success >= n and n_other <= 0.02 * (n_success + n_other), (n_success, n_other)
+    assert 30 <= np.min(lens) and np.max(lens) <= 800 and 200 <= np.median(lens) <= 520, (np.min(lens), np.median(lens), np.max(lens))
+    assert 1500 <= np.median(rets) <= 6000
+    env.close()

@@ -337,6 +337,10 @@ def run_gpu(args) -> None:
             step_events[i][1].record()
     torch.cuda.synchronize()
     step_kernel_ms = statistics.median(a.elapsed_time(b) for a, b in step_events)
+    if policy is None:
+        # bare-step workload: a step IS one launch of this kernel, so the graph-replayed step time is its duration without
+        # the host launch gap the event-bracketed eager pass includes
+        step_kernel_ms = min(step_kernel_ms, ms_total / args.steps)
     policy_kernel_ms = statistics.median(a.elapsed_time(b) for a, b in policy_events) if policy is not None else None
 
     # ---- end to end through the SB3-style VecEnv call: pinned host actions in, obs/reward/done out --------

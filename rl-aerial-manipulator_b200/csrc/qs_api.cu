@@ -161,13 +161,13 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     size_t bytes = 0;
     QS_DISPATCH(h, bytes = pool_bytes<Real, VER>(cfg->n_envs); h->bytes_per_env = PoolLayout<Real, VER>::BYTES;);
     h->pool_bytes = bytes;
-    err = cudaMalloc(&h->pool, bytes);
+    err = cudaMalloc(&h->pool, bytes + 4096);   // slack: the TMA kernel rounds the last tile's tail-plane read up to 16 bytes
     if (err != cudaSuccess) {
         set_error(nullptr, "qs_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
         delete h;
         return QS_ENOMEM;
     }
-    cudaMemset(h->pool, 0, bytes);
+    cudaMemset(h->pool, 0, bytes + 4096);
     h->mom_scratch = nullptr;
     h->mom_out = nullptr;
     h->mom_stats = nullptr;

@@ -34,6 +34,13 @@ template <typename Real> QS_HD Real qs_sqrt(Real x);
 template <> QS_HD float qs_sqrt<float>(float x) { return sqrtf(x); }
 template <> QS_HD double qs_sqrt<double>(double x) { return sqrt(x); }
 
+// 1/x: exact division in float64 and on the host; in float32 device code MUFU.RCP + one Newton step (__frcp_rn), which
+// keeps the IEEE-division slow path (FCHK + call) out of the four-stage RK4 loop
+template <typename Real> QS_HD Real qs_rcp(Real x) { return Real(1) / x; }
+#if defined(__CUDA_ARCH__) && !defined(QS_EXACT_F32_DIV)
+template <> QS_HD float qs_rcp<float>(float x) { return __frcp_rn(x); }
+#endif
+
 template <typename Real> QS_HD Real qs_min(Real a, Real b) { return a < b ? a : b; }
 template <typename Real> QS_HD Real qs_max(Real a, Real b) { return a > b ? a : b; }
 
@@ -71,7 +78,7 @@ QS_HD void state_dot(const Model<Real>& m, const Real* y, Real F, const Real* M,
         dy[4] = (Real)(im * (r21 * (double)F));
         dy[5] = (Real)(im * (r22 * (double)F - (double)m.mass * (double)m.g));
     } else {
-        const Real inv_n2 = Real(1) / n2;
+        const Real inv_n2 = qs_rcp<Real>(n2);
         const Real fm = F * m.inv_mass;
         dy[3] = (Real(2) * (qx * qz - qw * qy) * inv_n2) * fm;
         dy[4] = (Real(2) * (qy * qz + qw * qx) * inv_n2) * fm;
@@ -169,7 +176,12 @@ QS_HD void rk4_step(const Model<Real>& m, Real* y, Real F, const Real* M, int su
 template <typename Real>
 QS_HD void renormalise_quat(Real* y) {
     const Real n = qs_sqrt<Real>(y[6] * y[6] + y[7] * y[7] + y[8] * y[8] + y[9] * y[9]);
-    y[6] /= n; y[7] /= n; y[8] /= n; y[9] /= n;
+    if (sizeof(Real) == 4) {
+        const Real r = qs_rcp<Real>(n);
+        y[6] *= r; y[7] *= r; y[8] *= r; y[9] *= r;
+    } else {
+        y[6] /= n; y[7] /= n; y[8] /= n; y[9] /= n;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

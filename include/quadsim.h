@@ -207,6 +207,17 @@ int qs_policy_forward(const float* params, int obs_dim, const float* obs, const 
                       float* values, float* logp, int impl, void* stream);
 const char* qs_policy_last_error(void);
 
+/* Generalized advantage estimation ------------------------------------------------------------------
+ * Replaces stable_baselines3 RolloutBuffer.compute_returns_and_advantage (inside model.learn(), reference call sites
+ * initial-implementation-v1/rl_train_vecN.py:36, initial-implementation-v2/rl_train.py:56; gamma 0.995, gae_lambda 0.9).
+ * All buffers time-major [T, n] on the device: rewards/values f32, episode_starts u8 (1 where the env was reset before step t),
+ * last_values f32[n] / last_dones u8[n] for the state after the last step.  Writes advantages and returns f32[T, n].
+ */
+int qs_gae(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values,
+           const uint8_t* last_dones, int T, int64_t n, float gamma, float gae_lambda, float* advantages, float* returns,
+           void* stream);
+const char* qs_gae_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,18 @@
+"""On-device PPO run (tools, not a test): prints ep_rew_mean per iteration.
+python tools/train_demo.py [n_envs] [iters] [n_steps] [batch] [epochs] [env_version]"""
+import os, sys, time
+sys.path.insert(0, os.getcwd())
+import torch
+from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+from rl_aerial_manipulator_b200.ppo import QuadPPO
+arg = lambda i, d: int(sys.argv[i]) if len(sys.argv) > i else d
+n, iters, n_steps, batch, epochs, ver = arg(1, 16384), arg(2, 30), arg(3, 128), arg(4, 0), arg(5, 4), arg(6, 2)
+env = BatchedQuadEnv(n, env_version=ver, precision="f32", seed=0)
+ppo = QuadPPO(env, n_steps=n_steps, batch_size=batch or n * n_steps // 32, n_epochs=epochs, learning_rate=2e-4, ent_coef=0.01, seed=0)
+t0 = time.time()
+k = [0]
+def log(d):
+    k[0] += 1
+    if k[0] % max(1, iters // 25) == 0 or k[0] == 1:
+        print(f"steps {d['timesteps']:.3e}  ep_rew_mean {d['ep_rew_mean']:9.2f} ({d['episodes']} eps)  loss {d['loss']:10.3f}  vf {d['value_loss']:10.3f}  t {time.time()-t0:6.1f}s", flush=True)
+ppo.learn(iters * n_steps * n, log=log)

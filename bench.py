@@ -281,7 +281,7 @@ def run_gpu(args) -> None:
     barrier()
     # CUDA-graph replay of the step loop (4 steps per graph, so the 4 action / noise buffers rotate exactly as in eager
     # mode): removes the host launch path (Python -> ctypes -> cudaLaunch, ~5 launches per step) from the critical path
-    unroll = 4 if (args.graph and args.steps % 4 == 0) else 0
+    unroll = (4 if args.steps % 4 == 0 else 2 if args.steps % 2 == 0 else 1) if args.graph else 0   # exactly K steps are timed
     graph = None
     if unroll:
         side = torch.cuda.Stream(device=dev)

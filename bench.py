@@ -397,7 +397,7 @@ def run_gpu(args) -> None:
             roofline = {"bound": "tensor", "kernel": "policy_forward_tc_kernel<20,split-f16>", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
                         "frac": tach / tpeak, "traffic": ncu_traffic("policy_forward_tc_kernel"), "peak_source": tsrc,
                         "algorithmic_flops_per_env_step": POLICY_FLOPS, "kernel_ms": policy_kernel_ms,
-                        "note": "epilogue-bound (2 MUFU per tanh, 512 tanh per env): ncu shows the XU pipe, not the tensor pipe, as the limiter"}
+                        "note": "epilogue-bound (1.25 MUFU per tanh, 512 tanh per env, serial MMA->epilogue chain per 128-env tile): the XU pipe and the chain latency, not the tensor pipe, are the limiters"}
             roofline_other = [step_roofline]
         base = None
         if world == 1 and not args.no_cpu_baseline:

@@ -22,8 +22,15 @@
 //     [192,200)  the constant chunk (1, 0, ..., 0): A operand of the bias k-step of layers 2 and 3
 //     [224,256)  observation tile, hi | lo  (A operand of layer 1, kept for both nets); column k = OBS holds 1.0 (bias)
 // In PRECISE mode weights and biases are pre-multiplied by 2*log2(e), so the accumulator IS the exponent of
-// tanh(x) = 1 - 2/(2^acc + 1): the epilogue is MUFU.EX2, FADD, MUFU.RCP, FFMA, then the hi/lo split (LOP3, FADD, 2 F2FP per pair).
-// so hidden activations never touch shared memory: tcgen05.ld -> registers -> bias, tanh, split -> tcgen05.st.
+// tanh(x) = 1 - 2/(2^acc + 1); four elements share one reciprocal (tanh4_from_exponents): 5 MUFU per 4 tanh, then the hi/lo
+// split (LOP3, FADD, 2 F2FP per pair).  Hidden activations never touch shared memory: tcgen05.ld -> registers -> tanh, split
+// -> tcgen05.st.
+//
+// Scheduling, as measured with the clock64 phase trace (QS_TC_TRACE, tools/policy_trace.py): a tile is a serial chain
+// MMA -> epilogue -> MMA ... per group, so the two groups are the only overlap there is.  (1) The MMAs are issued by an elected
+// lane under a WARP-UNIFORM branch: from a divergent `if (thread == 0)` each UTCHMMA cost an ELECT/R2UR waterfall (~100 cycles
+// per MMA, 8.7k of a tile's 23k cycles).  (2) The groups take turns on the MUFU-bound part of the epilogues (named barriers).
+// (3) The observation rows of the CTA's next tile are prefetched into L2 while the current tile computes.
 #include "../../include/quadsim.h"
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -46,6 +53,15 @@ constexpr int C_B1 = 0, C_B2 = C_B1 + 2 * N1, C_B3 = C_B2 + 2 * N2, C_WH = C_B3 
               C_LS = C_BH + 2 * NACT, C_TOTAL = C_LS + NACT;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_R1 = 0, COL_R2 = 128, COL_ONE = 192, COL_X = 224;
+
+// QS_TC_TRACE (experimental builds only): threads 0 and 32 of each group of CTA 0 stamp clock64 at every phase boundary of their
+// fourth tile; qs_policy_debug_trace() copies the stamps out.  See tools/policy_trace.py.
+#ifdef QS_TC_TRACE
+__device__ long long g_trace[2][2][64];
+#define QS_TR() do { if (tr_on && tr_i < 64) g_trace[g][tg >> 5][tr_i++] = clock64(); } while (0)
+#else
+#define QS_TR() do { } while (0)
+#endif
 
 struct Blob {
     int obs;
@@ -79,6 +95,20 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp.  The MMA issue runs under a warp-uniform branch + this election so that descriptors and TMEM
+// addresses stay in uniform registers: issued from a divergent `if (thread == 0)`, every UTCHMMA costs an ELECT/R2UR waterfall
+// loop (~100 cycles per MMA measured, 8.7k of the 23k cycles a tile took).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -104,8 +134,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // (MUFU-bound) only while it holds the turn, so the other group's MMA wait / loads / stores fall under it instead of both
 // groups idling the XU pipe at the same moments.  Barrier 3+g is "group g may run its epilogue": g syncs on it, the other
 // group arrives on it when its own epilogue ends.
+#ifdef QS_TC_EXPERIMENT_NO_TURNS     // timing experiment only: both groups free-running
+__device__ __forceinline__ void turn_wait(int) {}
+__device__ __forceinline__ void turn_pass(int) {}
+#else
 __device__ __forceinline__ void turn_wait(int g) { asm volatile("bar.sync %0, 512;" ::"r"(3 + g) : "memory"); }
 __device__ __forceinline__ void turn_pass(int g) { asm volatile("bar.arrive %0, 512;" ::"r"(3 + (g ^ 1)) : "memory"); }
+#endif
+// The turn starts once the accumulator chunk is in registers (the TMEM load needs no turn).  QS_TC_WIDE_TURN=1: it ends after
+// the activations are stored back; 0: right after the tanh math (split + TMEM store under the other group's turn).
+#ifndef QS_TC_WIDE_TURN
+#define QS_TC_WIDE_TURN 1
+#endif
+__device__ __forceinline__ void turn_pass_wide(int g) { if (QS_TC_WIDE_TURN) turn_pass(g); }
+__device__ __forceinline__ void turn_pass_narrow(int g) { if (!QS_TC_WIDE_TURN) turn_pass(g); }
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
@@ -118,7 +160,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the loaded registers are valid only after this; tying them to the asm keeps the compiler from hoisting their uses above it
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
@@ -142,6 +193,46 @@ __device__ __forceinline__ float tanh_from_exponent(float u) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(u));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
     return fmaf(-2.0f, r, 1.0f);
+}
+// Four tanh on one MUFU.RCP: with a_i = 2^min(u_i,30) + 1 (tanh is 1.0f to the last bit beyond u = 30, and the clamp keeps
+// the product of four below 2^124), 1/a = (b*c*d) / (a*b*c*d).  5 MUFU per 4 elements instead of 8; the extra FMULs run on the
+// FMA pipe, which the epilogue leaves idle.  Error: ~3 ulp of 1/a <= 2e-7 absolute.
+#ifndef QS_TC_RCP_SHARE
+#define QS_TC_RCP_SHARE 4
+#endif
+__device__ __forceinline__ void tanh4_from_exponents(const uint32_t* v, float* y) {
+    float a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float t, u;
+        asm("min.NaN.f32 %0, %1, %2;" : "=f"(u) : "f"(__uint_as_float(v[i])), "f"(30.0f));   // NaN stays NaN, like torch
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(u));
+        a[i] = t + 1.0f;
+    }
+    const float p = a[0] * a[1], q = a[2] * a[3];
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p * q));
+    r *= -2.0f;
+    const float rp = r * q, rq = r * p;      // -2/(a0 a1), -2/(a2 a3)
+    y[0] = fmaf(rp, a[1], 1.0f);
+    y[1] = fmaf(rp, a[0], 1.0f);
+    y[2] = fmaf(rq, a[3], 1.0f);
+    y[3] = fmaf(rq, a[2], 1.0f);
+}
+__device__ __forceinline__ void tanh2_from_exponents(const uint32_t* v, float* y) {   // A/B variant: 3 MUFU per 2 elements
+    float a[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float t, u;
+        asm("min.NaN.f32 %0, %1, %2;" : "=f"(u) : "f"(__uint_as_float(v[i])), "f"(60.0f));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(u));
+        a[i] = t + 1.0f;
+    }
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[0] * a[1]));
+    r *= -2.0f;
+    y[0] = fmaf(r, a[1], 1.0f);
+    y[1] = fmaf(r, a[0], 1.0f);
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -191,16 +282,23 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ w, const
     }
 }
 
-// one 32-column accumulator chunk of this thread's row (bias already inside) -> tanh (float32 in y)
+// one loaded 32-column accumulator chunk of this thread's row (bias already inside) -> tanh (float32 in y)
 template <bool PRECISE>
-__device__ __forceinline__ void act32(uint32_t taddr, float* y) {
-    uint32_t v[32];
-    tmem_ld32(taddr, v);
-#pragma unroll
+__device__ __forceinline__ void tanh32(const uint32_t* v, float* y) {
 #ifdef QS_TC_EXPERIMENT_NO_TANH   // timing experiment only: how much of the kernel is XU work
+#pragma unroll
     for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]) * 0.001f;
 #else
-    for (int i = 0; i < 32; ++i) y[i] = PRECISE ? tanh_from_exponent(__uint_as_float(v[i])) : tanh_mufu(__uint_as_float(v[i]));
+    if (PRECISE && QS_TC_RCP_SHARE == 4) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) tanh4_from_exponents(v + i, y + i);
+    } else if (PRECISE && QS_TC_RCP_SHARE == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) tanh2_from_exponents(v + i, y + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = PRECISE ? tanh_from_exponent(__uint_as_float(v[i])) : tanh_mufu(__uint_as_float(v[i]));
+    }
 #endif
 }
 
@@ -291,6 +389,12 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // warp-uniform copies for the MMA issuer (first warp of each group): everything the MMAs take derives from these
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g_u = warp_u >> 3;
+    const bool issuer_warp = (warp_u & 7) == 0;
+    const uint32_t tmem_u = s_tmem_base + (uint32_t)g_u * 256u;
+    const uint32_t bar_u = smem_u32(&s_bars[0]) + 8u * (uint32_t)g_u;
     const uint32_t tmem = s_tmem_base + (uint32_t)g * 256u;             // this group's 256 columns (lane field 0)
     const uint32_t lane_addr = tmem + ((uint32_t)(t & ~31) << 16);     // this warp's lane quadrant
     const uint32_t bar = smem_u32(&s_bars[g]);
@@ -318,14 +422,34 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
         }
         const int64_t e = tile * ROWS + t;
         const bool live = e < p.n;
+#ifdef QS_TC_TRACE
+        const bool tr_on = blockIdx.x == 0 && tile0 == (int64_t)gridDim.x * GROUPS * 3 && (tg == 0 || tg == 32);
+        int tr_i = 0;
+#endif
+        QS_TR();                                                        // 0: tile start
         if (half == 0) {   // observation row -> (normalise) -> split float16 -> TMEM columns [224,256)
             float x[K1];
 #pragma unroll
             for (int k = 0; k < K1; ++k) x[k] = 0.f;
             if (live) {
                 const float* row = p.obs + e * OBS;
+                if (OBS % 4 == 0) {                                     // 80-byte rows: five 16-byte loads
 #pragma unroll
-                for (int k = 0; k < OBS; ++k) x[k] = __ldcs(row + k);
+                    for (int k = 0; k < OBS / 4; ++k) {
+                        const float4 q = __ldcs(reinterpret_cast<const float4*>(row) + k);
+                        x[4 * k] = q.x; x[4 * k + 1] = q.y; x[4 * k + 2] = q.z; x[4 * k + 3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < OBS; ++k) x[k] = __ldcs(row + k);
+                }
+                // this thread's row of the CTA's next tile: pull it into L2 now, the load above is the exposed part of a tile
+                const int64_t e_next = e + (int64_t)gridDim.x * GROUPS * ROWS;
+                if (e_next < p.n) {
+                    const char* nr = reinterpret_cast<const char*>(p.obs + e_next * OBS);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nr));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + OBS * 4 - 4));
+                }
                 if (p.norm) {
 #pragma unroll
                     for (int k = 0; k < OBS; ++k) {
@@ -353,68 +477,108 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
 #pragma unroll 1
         for (int net = 0; net < 2; ++net) {
             // ---------------- layer 1: X[128 x 32] . W1^T -> R1[128 columns]
-            if (tg == 0) {
+            QS_TR();                                                    // a: before issue
+            if (issuer_warp) {
                 tc_fence_after();
-                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_X, K1, sbase + OFF_W1 + net * W1_BYTES, sbase + OFF_LO + OFF_W1 + net * W1_BYTES, B1_LBO, N1, 0);
-                umma_commit(bar);
+                if (elect_one()) {
+                    issue_layer<PRECISE>(tmem_u + COL_R1, tmem_u + COL_X, K1, sbase + OFF_W1 + net * W1_BYTES, sbase + OFF_LO + OFF_W1 + net * W1_BYTES, B1_LBO, N1, 0);
+                    umma_commit(bar_u);
+                }
             }
+            QS_TR();                                                    // b: issued
             __syncwarp();
             mbar_wait(bar, phase);
             phase ^= 1;
             __syncwarp();
             tc_fence_after();
-            turn_wait(g);
-#pragma unroll 1
-            for (int cb = half; cb < N1 / 32; cb += 2) {
-                float y[32];
-                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, y);
-                put32<PRECISE>(lane_addr + COL_R1 + cb * 32, y);        // in place: hi | lo
-            }
-            turn_pass(g);
-            tmem_st_wait();
-            tc_fence_before();
-            group_bar(g);
-            // ---------------- layer 2: H1[128 x 128] . W2^T -> R2[64 columns]
-            if (tg == 0) {
-                tc_fence_after();
-                issue_layer<PRECISE>(tmem + COL_R2, tmem + COL_R1, N1, sbase + OFF_W2 + net * W2_BYTES, sbase + OFF_LO + OFF_W2 + net * W2_BYTES, B2_LBO, N2, tmem + COL_ONE);
-                umma_commit(bar);
-            }
-            __syncwarp();
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            __syncwarp();
-            tc_fence_after();
-            turn_wait(g);
+            QS_TR();                                                    // c: MMAs complete
+            // The turn covers the MUFU work only; TMEM loads, the hi/lo split and the TMEM stores run outside it (or under
+            // the next load), i.e. under the other group's tanh.  This thread's chunks: half and half + 2 of the four.
             {
-                const int cb = half;
+                static_assert(N1 / 32 == 4, "two chunks per thread");
+                uint32_t v[32];
                 float y[32];
-                act32<PRECISE>(lane_addr + COL_R2 + cb * 32, y);
-                put32<PRECISE>(lane_addr + COL_R2 + cb * 32, y);
+                const uint32_t c0 = lane_addr + COL_R1 + half * 32, c1 = c0 + 64;
+                tmem_ld32(c0, v);
+                tmem_ld_wait32(v);
+                turn_wait(g);
+                QS_TR();                                                // d: loaded, has the turn
+                tanh32<PRECISE>(v, y);
+                tmem_ld32(c1, v);
+                put32<PRECISE>(c0, y);                                   // in place: hi | lo
+                tmem_ld_wait32(v);
+                tanh32<PRECISE>(v, y);
+                turn_pass_narrow(g);
+                put32<PRECISE>(c1, y);
+                turn_pass_wide(g);
             }
-            turn_pass(g);
+            QS_TR();                                                    // e: epilogue done
             tmem_st_wait();
             tc_fence_before();
             group_bar(g);
-            // ---------------- layer 3: H2[128 x 64] . W3^T -> R1[first 64 columns], then the float32 head
-            if (tg == 0) {
+            QS_TR();                                                    // f: group barrier passed
+            // ---------------- layer 2: H1[128 x 128] . W2^T -> R2[64 columns]
+            QS_TR();
+            if (issuer_warp) {
                 tc_fence_after();
-                issue_layer<PRECISE>(tmem + COL_R1, tmem + COL_R2, N2, sbase + OFF_W3 + net * W3_BYTES, sbase + OFF_LO + OFF_W3 + net * W3_BYTES, B2_LBO, N3, tmem + COL_ONE);
-                umma_commit(bar);
+                if (elect_one()) {
+                    issue_layer<PRECISE>(tmem_u + COL_R2, tmem_u + COL_R1, N1, sbase + OFF_W2 + net * W2_BYTES, sbase + OFF_LO + OFF_W2 + net * W2_BYTES, B2_LBO, N2, tmem_u + COL_ONE);
+                    umma_commit(bar_u);
+                }
             }
+            QS_TR();                                                    // b: issued
             __syncwarp();
             mbar_wait(bar, phase);
             phase ^= 1;
             __syncwarp();
             tc_fence_after();
+            QS_TR();                                                    // c: MMAs complete
+            {
+                uint32_t v[32];
+                float y[32];
+                tmem_ld32(lane_addr + COL_R2 + half * 32, v);
+                tmem_ld_wait32(v);
+                turn_wait(g);
+                QS_TR();                                                // d: loaded, has the turn
+                tanh32<PRECISE>(v, y);
+                turn_pass_narrow(g);
+                put32<PRECISE>(lane_addr + COL_R2 + half * 32, y);
+                turn_pass_wide(g);
+            }
+            QS_TR();                                                    // e: epilogue done
+            tmem_st_wait();
+            tc_fence_before();
+            group_bar(g);
+            QS_TR();                                                    // f: group barrier passed
+            // ---------------- layer 3: H2[128 x 64] . W3^T -> R1[first 64 columns], then the float32 head
+            QS_TR();
+            if (issuer_warp) {
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_layer<PRECISE>(tmem_u + COL_R1, tmem_u + COL_R2, N2, sbase + OFF_W3 + net * W3_BYTES, sbase + OFF_LO + OFF_W3 + net * W3_BYTES, B2_LBO, N3, tmem_u + COL_ONE);
+                    umma_commit(bar_u);
+                }
+            }
+            QS_TR();                                                    // b: issued
+            __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            __syncwarp();
+            tc_fence_after();
+            QS_TR();                                                    // c: MMAs complete
             float o[NACT];
 #pragma unroll
             for (int j = 0; j < NACT; ++j) o[j] = half == 0 ? sC[C_BH + net * NACT + j] : 0.f;
-            turn_wait(g);
             {
                 const int cb = half;
+                uint32_t v[32];
                 float y[32];
-                act32<PRECISE>(lane_addr + COL_R1 + cb * 32, y);
+                tmem_ld32(lane_addr + COL_R1 + cb * 32, v);
+                tmem_ld_wait32(v);
+                turn_wait(g);
+                QS_TR();                                                // d: loaded, has the turn
+                tanh32<PRECISE>(v, y);
+                turn_pass(g);                                           // the float32 head below is FMA-pipe work: outside the turn
                 const float4* wh = reinterpret_cast<const float4*>(sC + C_WH + net * N3 * NACT + cb * 32 * NACT);
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
@@ -425,10 +589,11 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
                     o[3] = fmaf(y[k], w.w, o[3]);
                 }
             }
-            turn_pass(g);
             if (half == 1) *reinterpret_cast<float4*>(&s_part[g][t][0]) = make_float4(o[0], o[1], o[2], o[3]);
+            QS_TR();
             tc_fence_before();   // the next MMAs overwrite TMEM columns this thread has just read
             group_bar(g);
+            QS_TR();
             if (half == 0) {
                 const float4 q = *reinterpret_cast<const float4*>(&s_part[g][t][0]);
                 if (net == 0) {
@@ -472,6 +637,12 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
 }
 
 }  // namespace tc
+
+#ifdef QS_TC_TRACE
+extern "C" int qs_policy_debug_trace(long long* out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, tc::g_trace, sizeof(tc::g_trace));
+}
+#endif
 
 thread_local char g_policy_tc_error[256] = "";
 

@@ -218,6 +218,29 @@ int qs_gae(const float* rewards, const float* values, const uint8_t* episode_sta
            void* stream);
 const char* qs_gae_last_error(void);
 
+/* Batched PID baseline controller ----------------------------------------------------------------------
+ * Replaces `run(quad, des_state, dt)` of initial-implementation-v2/PID Controller/pid_controller.py:37-115 for all envs of a
+ * handle at once: position PID -> commanded acceleration -> thrust F and desired roll/pitch; attitude PID -> moments M.
+ * The reference keeps one module-level `integral_error` dict (:24-31); here the six integrals per env are a caller-owned
+ * buffer, updated in place (clamped to +-max_integral like :65-66, :105-106).  The vehicle state (position, velocity,
+ * quaternion, body rates) is read from the handle's state pool; the attitude is RotToRPY of the Rodrigues matrix like
+ * Quadcopter.attitude() (PID Controller/model/quadcopter.py:58-60).  All arithmetic is float64.
+ * Gains in the order x, y, z, phi, theta, psi; qs_pid_default_gains() writes the reference's (:16-22, :34).
+ * Desired state: des_pos f64[n,3] or NULL = each env's current waypoint (hover target); des_vel / des_acc f64[n,3] and
+ * des_yaw / des_yawdot f64[n], NULL = zeros (des_yaw NULL on a v2 handle = the env's final_yaw).
+ * Outputs (each optional): wrench_out f64[n,4] = (F, M1, M2, M3) exactly as the reference returns them; actions_out f32[n,4] =
+ * the env action that commands this wrench, a0 = F/(mass*g), a[1:4] = M/0.1 (inverse of rl_env_scaledObs.py:125-126), clipped
+ * to the action box [0,2]x[-1,1]^3 when clip_actions != 0 -- feed it to qs_step.
+ */
+typedef struct qs_pid_gains {
+    double kp[6], kd[6], ki[6];
+    double max_integral;
+} qs_pid_gains;
+void qs_pid_default_gains(qs_pid_gains* out);
+int qs_pid_run(qs_handle* h, const qs_pid_gains* gains, double dt, const double* des_pos, const double* des_vel,
+               const double* des_acc, const double* des_yaw, const double* des_yawdot, double* integral,
+               double* wrench_out, float* actions_out, int clip_actions, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,11 @@ def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", subs
     return c
 
 
+class QsPidGains(C.Structure):
+    """qs_pid_gains of include/quadsim.h (order x, y, z, phi, theta, psi)."""
+    _fields_ = [("kp", C.c_double * 6), ("kd", C.c_double * 6), ("ki", C.c_double * 6), ("max_integral", C.c_double)]
+
+
 _lib = None
 
 
@@ -108,6 +113,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.qs_set_state.argtypes = [vp, C.POINTER(QsStateView), vp]
     lib.qs_reset_uniforms.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.qs_lsoda_stats.argtypes = [vp, vp, vp, vp]
+    lib.qs_pid_default_gains.argtypes = [C.POINTER(QsPidGains)]
+    lib.qs_pid_default_gains.restype = None
+    lib.qs_pid_run.argtypes = [vp, C.POINTER(QsPidGains), C.c_double] + [vp] * 8 + [i32, vp]
+    lib.qs_pid_run.restype = C.c_int
     for name in ("qs_create", "qs_destroy", "qs_obs_dim", "qs_reset", "qs_step", "qs_get_state", "qs_set_state",
                  "qs_reset_uniforms", "qs_lsoda_stats", "qs_step_moments"):
         getattr(lib, name).restype = C.c_int

@@ -60,6 +60,13 @@ constexpr int STEP_BLOCK = 128;
 #define QS_STEP_PREFETCH_F32 1
 #endif
 template <typename Real, int INTEG> struct StepOcc { static constexpr int MINB = 1; static constexpr bool PREFETCH = false; };
+#ifndef QS_STEP_MINB_F64
+#define QS_STEP_MINB_F64 3
+#endif
+#ifndef QS_STEP_PREFETCH_F64
+#define QS_STEP_PREFETCH_F64 0
+#endif
+template <> struct StepOcc<double, 0> { static constexpr int MINB = QS_STEP_MINB_F64; static constexpr bool PREFETCH = QS_STEP_PREFETCH_F64 != 0; };
 template <> struct StepOcc<float, 0> { static constexpr int MINB = QS_STEP_MINB_F32; static constexpr bool PREFETCH = QS_STEP_PREFETCH_F32 != 0; };
 
 // Row-major [32, OBS] tile of one warp -> global, 128 bits per lane per store.

@@ -30,7 +30,8 @@
 // MMA -> epilogue -> MMA ... per group, so the two groups are the only overlap there is.  (1) The MMAs are issued by an elected
 // lane under a WARP-UNIFORM branch: from a divergent `if (thread == 0)` each UTCHMMA cost an ELECT/R2UR waterfall (~100 cycles
 // per MMA, 8.7k of a tile's 23k cycles).  (2) The groups take turns on the MUFU-bound part of the epilogues (named barriers).
-// (3) The observation rows of the CTA's next tile are prefetched into L2 while the current tile computes.
+// (3) The observation tile is staged one tile ahead (loaded, normalised, split and stored to TMEM by the half of the group that
+// does not issue MMAs, while the critic's layer-2 MMAs run); the tile after that is prefetched into L2.
 #include "../../include/quadsim.h"
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -54,11 +55,11 @@ constexpr int C_B1 = 0, C_B2 = C_B1 + 2 * N1, C_B3 = C_B2 + 2 * N2, C_WH = C_B3 
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_R1 = 0, COL_R2 = 128, COL_ONE = 192, COL_X = 224;
 
-// QS_TC_TRACE (experimental builds only): threads 0 and 32 of each group of CTA 0 stamp clock64 at every phase boundary of their
+// QS_TC_TRACE (experimental builds only): threads 0 and 128 (the MMA issuer) of each group of CTA 0 stamp clock64 at every phase boundary of their
 // fourth tile; qs_policy_debug_trace() copies the stamps out.  See tools/policy_trace.py.
 #ifdef QS_TC_TRACE
 __device__ long long g_trace[2][2][64];
-#define QS_TR() do { if (tr_on && tr_i < 64) g_trace[g][tg >> 5][tr_i++] = clock64(); } while (0)
+#define QS_TR() do { if (tr_on && tr_i < 64) g_trace[g][tg >> 7][tr_i++] = clock64(); } while (0)
 #else
 #define QS_TR() do { } while (0)
 #endif
@@ -341,6 +342,51 @@ __device__ __forceinline__ void issue_layer(uint32_t d_col, uint32_t a_col, int 
     }
 }
 
+// Observation row e -> (normalise) -> split float16 -> this lane's TMEM columns [COL_X, COL_X + 32): the A operand of layer 1.
+// Also pulls the row this thread will need one tile later into L2.
+template <int OBS, bool PRECISE>
+__device__ __forceinline__ void stage_obs_row(const Args& p, int64_t e, bool live, int64_t tile_stride_rows, uint32_t x_addr,
+                                              const double* s_mean, const double* s_istd) {
+    float x[K1];
+#pragma unroll
+    for (int k = 0; k < K1; ++k) x[k] = 0.f;
+    if (live) {
+        const float* row = p.obs + e * OBS;
+        if (OBS % 4 == 0) {                                     // 80-byte rows: five 16-byte loads
+#pragma unroll
+            for (int k = 0; k < OBS / 4; ++k) {
+                const float4 q = __ldcs(reinterpret_cast<const float4*>(row) + k);
+                x[4 * k] = q.x; x[4 * k + 1] = q.y; x[4 * k + 2] = q.z; x[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < OBS; ++k) x[k] = __ldcs(row + k);
+        }
+        const int64_t e_next = e + tile_stride_rows;
+        if (e_next < p.n) {
+            const char* nr = reinterpret_cast<const char*>(p.obs + e_next * OBS);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nr));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + OBS * 4 - 4));
+        }
+        if (p.norm) {
+#pragma unroll
+            for (int k = 0; k < OBS; ++k) {
+                float v = (float)(((double)x[k] - s_mean[k]) * s_istd[k]);
+                x[k] = fminf(fmaxf(v, -p.norm_clip), p.norm_clip);
+            }
+            if (p.obs_norm_out) {
+                float* orow = p.obs_norm_out + e * OBS;
+#pragma unroll
+                for (int k = 0; k < OBS; ++k) orow[k] = x[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < OBS; ++k) x[k] = fminf(fmaxf(x[k], -60000.f), 60000.f);   // float16 range
+    }
+    x[OBS] = 1.0f;                                              // multiplies the bias row of W1
+    put32<PRECISE>(x_addr, x);
+}
+
 template <int OBS, bool PRECISE>
 __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Args p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -389,10 +435,10 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // warp-uniform copies for the MMA issuer (first warp of each group): everything the MMAs take derives from these
+    // warp-uniform copies for the MMA issuer (one warp of each group): everything the MMAs take derives from these
     const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g_u = warp_u >> 3;
-    const bool issuer_warp = (warp_u & 7) == 0;
+    const bool issuer_warp = (warp_u & 7) == 4;                       // a warp of the half that does not stage observations
     const uint32_t tmem_u = s_tmem_base + (uint32_t)g_u * 256u;
     const uint32_t bar_u = smem_u32(&s_bars[0]) + 8u * (uint32_t)g_u;
     const uint32_t tmem = s_tmem_base + (uint32_t)g * 256u;             // this group's 256 columns (lane field 0)
@@ -411,10 +457,23 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
         tmem_st_wait();
     }
     const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
+    const int64_t tile_stride = (int64_t)gridDim.x * GROUPS;
     if (g == 1) turn_pass(1);                                          // group 0 takes the first turn
+    // The observation tile is staged one tile ahead: the first one here, every later one inside the previous tile while the
+    // layer-2 MMAs of its critic run (X is dead once the critic's layer-1 MMAs have completed).
+    {
+        const int64_t tile = (int64_t)blockIdx.x * GROUPS + g;
+        if (tile < n_tiles && half == 0) {
+            const int64_t e = tile * ROWS + t;
+            stage_obs_row<OBS, PRECISE>(p, e, e < p.n, tile_stride * ROWS, lane_addr + COL_X, s_mean, s_istd);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        group_bar(g);
+    }
     // both groups run the same number of rounds (group 0 never has fewer tiles); a group without a tile in the last
     // round only keeps the turn moving
-    for (int64_t tile0 = (int64_t)blockIdx.x * GROUPS; tile0 < n_tiles; tile0 += (int64_t)gridDim.x * GROUPS) {
+    for (int64_t tile0 = (int64_t)blockIdx.x * GROUPS; tile0 < n_tiles; tile0 += tile_stride) {
         const int64_t tile = tile0 + g;
         if (tile >= n_tiles) {
             for (int k = 0; k < 6; ++k) { turn_wait(g); turn_pass(g); }
@@ -423,55 +482,10 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
         const int64_t e = tile * ROWS + t;
         const bool live = e < p.n;
 #ifdef QS_TC_TRACE
-        const bool tr_on = blockIdx.x == 0 && tile0 == (int64_t)gridDim.x * GROUPS * 3 && (tg == 0 || tg == 32);
+        const bool tr_on = blockIdx.x == 0 && tile0 == (int64_t)gridDim.x * GROUPS * 3 && (tg == 0 || tg == 128);
         int tr_i = 0;
 #endif
         QS_TR();                                                        // 0: tile start
-        if (half == 0) {   // observation row -> (normalise) -> split float16 -> TMEM columns [224,256)
-            float x[K1];
-#pragma unroll
-            for (int k = 0; k < K1; ++k) x[k] = 0.f;
-            if (live) {
-                const float* row = p.obs + e * OBS;
-                if (OBS % 4 == 0) {                                     // 80-byte rows: five 16-byte loads
-#pragma unroll
-                    for (int k = 0; k < OBS / 4; ++k) {
-                        const float4 q = __ldcs(reinterpret_cast<const float4*>(row) + k);
-                        x[4 * k] = q.x; x[4 * k + 1] = q.y; x[4 * k + 2] = q.z; x[4 * k + 3] = q.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < OBS; ++k) x[k] = __ldcs(row + k);
-                }
-                // this thread's row of the CTA's next tile: pull it into L2 now, the load above is the exposed part of a tile
-                const int64_t e_next = e + (int64_t)gridDim.x * GROUPS * ROWS;
-                if (e_next < p.n) {
-                    const char* nr = reinterpret_cast<const char*>(p.obs + e_next * OBS);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nr));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + OBS * 4 - 4));
-                }
-                if (p.norm) {
-#pragma unroll
-                    for (int k = 0; k < OBS; ++k) {
-                        float v = (float)(((double)x[k] - s_mean[k]) * s_istd[k]);
-                        x[k] = fminf(fmaxf(v, -p.norm_clip), p.norm_clip);
-                    }
-                    if (p.obs_norm_out) {
-                        float* orow = p.obs_norm_out + e * OBS;
-#pragma unroll
-                        for (int k = 0; k < OBS; ++k) orow[k] = x[k];
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < OBS; ++k) x[k] = fminf(fmaxf(x[k], -60000.f), 60000.f);   // float16 range
-            }
-            x[OBS] = 1.0f;                                              // multiplies the bias row of W1
-            put32<PRECISE>(lane_addr + COL_X, x);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        group_bar(g);
-
         float mean[NACT] = {0.f, 0.f, 0.f, 0.f};
         float value = 0.f;
 #pragma unroll 1
@@ -525,6 +539,10 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
                     issue_layer<PRECISE>(tmem_u + COL_R2, tmem_u + COL_R1, N1, sbase + OFF_W2 + net * W2_BYTES, sbase + OFF_LO + OFF_W2 + net * W2_BYTES, B2_LBO, N2, tmem_u + COL_ONE);
                     umma_commit(bar_u);
                 }
+            }
+            if (net == 1 && half == 0 && tile + tile_stride < n_tiles) {   // next tile's observations, under these MMAs
+                const int64_t en = (tile + tile_stride) * ROWS + t;
+                stage_obs_row<OBS, PRECISE>(p, en, en < p.n, tile_stride * ROWS, lane_addr + COL_X, s_mean, s_istd);
             }
             QS_TR();                                                    // b: issued
             __syncwarp();

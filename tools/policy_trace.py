@@ -24,6 +24,6 @@ for net in range(2):
     for l in (1, 2, 3):
         names += [f"n{net}L{l} pre-issue", f"n{net}L{l} issued", f"n{net}L{l} mma-done", f"n{net}L{l} turn", f"n{net}L{l} epi-done", f"n{net}L{l} grp-bar"]
 t0 = buf[buf > 0].min()
-print(f"{'event':18s} " + " ".join(f"g{g}t{t*32:<3d}      " for g in range(2) for t in range(2)))
+print(f"{'event':18s} " + " ".join(f"g{g}t{t*128:<3d}      " for g in range(2) for t in range(2)))
 for i, nm in enumerate(names):
     print(f"{nm:18s} " + " ".join(f"{int(buf[g, t, i] - t0):6d} ({int(buf[g, t, i] - buf[g, t, i - 1]) if i else 0:5d})" for g in range(2) for t in range(2)))

@@ -246,9 +246,10 @@ def run_gpu(args) -> None:
         policy = MlpPolicyKernel.from_npz(os.path.join(ROOT, "tests", "golden", "policy_v2.npz"), device=dev)
         launches_per_step = 2
         if args.vecnorm:
-            # VecNormalize(norm_obs=True): moments of this rank's shard -> all-gather of 2D+1 doubles over NCCL (N>1)
-            # -> Chan merge on device -> normalisation fused into the policy kernel's obs load
-            vn = DeviceRunningMeanStd(env.obs_dim, dev)
+            # VecNormalize(norm_obs=True): moments of this rank's shard -> (N>1) all-gather of 2D+1 doubles fused with the Chan
+            # merge in one kernel over NVLink peer memory (qs_xchg_merge; NCCL all-gather + merge kernel if peers cannot be
+            # mapped) -> normalisation fused into the policy kernel's obs load
+            vn = DeviceRunningMeanStd(env.obs_dim, dev, exchange=args.vecnorm_exchange)
             vn.attach(env)                                   # the step kernel reduces the obs it returns: no separate read pass
             launches_per_step = 4                            # env step + moments_final + merge + policy forward
     # uniform-random actions over the action box, pre-generated ring (step workload) / sampling noise (rollout)
@@ -342,6 +343,8 @@ def run_gpu(args) -> None:
         # the host launch gap the event-bracketed eager pass includes
         step_kernel_ms = min(step_kernel_ms, ms_total / args.steps)
     policy_kernel_ms = statistics.median(a.elapsed_time(b) for a, b in policy_events) if policy is not None else None
+    if vn is not None and vn.exchange_failed():
+        raise RuntimeError("peer-memory moment exchange timed out waiting for a rank; the timed region is invalid")
 
     # ---- end to end through the SB3-style VecEnv call: pinned host actions in, obs/reward/done out --------
     from rl_aerial_manipulator_b200.vec_env import QuadVecEnv
@@ -413,7 +416,8 @@ def run_gpu(args) -> None:
                            "vecnormalize": bool(vn is not None), "cuda_graph": bool(graph is not None),
                            "actions": "policy (ppo_model_2300000_steps weights, stochastic, clipped)" if policy else "uniform-random over the action box, 4 pre-generated device buffers",
                            "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
-                           "parallelism": f"env-shard x{world}, no data-path collective"},
+                           "parallelism": f"env-shard x{world}, no data-path collective",
+                           "moment_exchange": vn.exchange if vn is not None else "none"},
                 "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": base,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                         "api": "QuadVecEnv.step(actions: np.ndarray) -> obs, rewards, dones, infos (pinned staging, info_mode=lazy)"},
@@ -439,6 +443,8 @@ def main():
     ap.add_argument("--substeps", type=int, default=1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--vecnorm", type=int, default=1, help="rollout workload: update VecNormalize statistics every step (NCCL all-gather when N>1)")
+    ap.add_argument("--vecnorm-exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: how ranks exchange the VecNormalize moments (peer = fused all-gather+merge kernel over NVLink peer memory)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step loop from a CUDA graph (4 steps per graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)

@@ -218,6 +218,26 @@ int qs_gae(const float* rewards, const float* values, const uint8_t* episode_sta
            void* stream);
 const char* qs_gae_last_error(void);
 
+/* Peer-memory exchange of the VecNormalize moments (multi-GPU) --------------------------------------------
+ * The only exchange step of the sharded env path is the 2d+1 doubles (n, mean[d], M2[d]) each rank contributes to the running
+ * statistics per step.  qs_xchg_merge is that all-gather FUSED with the Chan merge in one kernel over NVLink peer memory: the
+ * rank stores its triplet straight into a slot of every peer's exchange buffer (P2P stores, release flag), waits until the
+ * slots of its own buffer carry this step's sequence number, and merges them in rank order into `stats` -- bit-identical on
+ * all ranks, no NCCL call, one launch, safe to capture in a CUDA graph (the sequence number lives on the device).
+ * Setup: every rank calls qs_xchg_create (allocates its buffer, returns a 64-byte CUDA IPC handle), the ranks exchange the
+ * handles by any host channel (torch.distributed.all_gather_object), then qs_xchg_connect maps the peers' buffers.
+ * All ranks must call qs_xchg_merge the same number of times; a rank that waits longer than ~2 s on a peer gives up, sets a
+ * sticky error (qs_xchg_failed() != 0) and merges what has arrived, so a dead peer cannot hang the GPU.
+ * The NCCL path (all_gather_into_tensor + qs_vecnorm_merge) stays available and is the one the gloo CPU tests cover.
+ */
+typedef struct qs_xchg qs_xchg;
+int qs_xchg_create(int device, int rank, int world, int d, qs_xchg** out, unsigned char* ipc_handle_out /*[64]*/);
+int qs_xchg_connect(qs_xchg* x, const unsigned char* all_handles /*[world][64], rank order*/);
+int qs_xchg_merge(qs_xchg* x, double* stats, const double* local_moments, void* stream);
+int qs_xchg_failed(qs_xchg* x);   /* synchronises the device; 1 if any merge timed out */
+int qs_xchg_destroy(qs_xchg* x);
+const char* qs_xchg_last_error(void);
+
 /* Batched PID baseline controller ----------------------------------------------------------------------
  * Replaces `run(quad, des_state, dt)` of initial-implementation-v2/PID Controller/pid_controller.py:37-115 for all envs of a
  * handle at once: position PID -> commanded acceleration -> thrust F and desired roll/pitch; attitude PID -> moments M.

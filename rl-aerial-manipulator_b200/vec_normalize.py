@@ -33,6 +33,14 @@ def _bind(lib):
     for f in ("qs_batch_moments", "qs_vecnorm_merge", "qs_vecnorm_apply", "qs_returns_update"):
         getattr(lib, f).restype = C.c_int
     lib.qs_vecnorm_last_error.restype = C.c_char_p
+    lib.qs_xchg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp]
+    lib.qs_xchg_connect.argtypes = [vp, C.c_char_p]
+    lib.qs_xchg_merge.argtypes = [vp, vp, vp, vp]
+    lib.qs_xchg_failed.argtypes = [vp]
+    lib.qs_xchg_destroy.argtypes = [vp]
+    for f in ("qs_xchg_create", "qs_xchg_connect", "qs_xchg_merge", "qs_xchg_failed", "qs_xchg_destroy"):
+        getattr(lib, f).restype = C.c_int
+    lib.qs_xchg_last_error.restype = C.c_char_p
     lib._vn_bound = True
 
 
@@ -57,7 +65,10 @@ def merge_moments(stats, moments):
 class DeviceRunningMeanStd:
     """stable_baselines3.common.running_mean_std.RunningMeanStd on the device."""
 
-    def __init__(self, dim: int, device, epsilon: float = 1e-4, group=None):
+    def __init__(self, dim: int, device, epsilon: float = 1e-4, group=None, exchange: str = "auto"):
+        """exchange (ranks > 1): how the per-rank batch moments meet.  "peer": qs_xchg_merge, the all-gather fused with the merge
+        in one kernel over NVLink peer memory; "nccl": all_gather_into_tensor + qs_vecnorm_merge; "auto": peer when every rank
+        could map its peers (CUDA IPC), else nccl."""
         self.lib = load_library()
         _bind(self.lib)
         self.dim, self.device, self.group = int(dim), torch.device(device), group
@@ -71,6 +82,47 @@ class DeviceRunningMeanStd:
         self._gathered = None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:   # pre-allocate: update() may run under graph capture
             self._gathered = torch.empty((dist.get_world_size(group), 1 + 2 * dim), dtype=torch.float64, device=self.device)
+        self._xchg = None
+        self.exchange = "none"
+        if self._gathered is not None:
+            if exchange not in ("auto", "peer", "nccl"):
+                raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+            self.exchange = "nccl"
+            if exchange != "nccl" and self.device.type == "cuda":
+                self._connect_peers(exchange == "peer")
+
+    def _connect_peers(self, required: bool) -> None:
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        x, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        rc = self.lib.qs_xchg_create(self.device.index, rank, world, self.dim, C.byref(x), handle)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle) if rc == 0 else None, group=self.group)
+        ok = rc == 0 and all(h is not None for h in handles)
+        if ok:
+            ok = self.lib.qs_xchg_connect(x, b"".join(handles)) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)          # every rank takes the same path
+        if int(flag.item()) == 1:
+            self._xchg, self.exchange = x, "peer"
+            return
+        why = self.lib.qs_xchg_last_error().decode()
+        if x:
+            self.lib.qs_xchg_destroy(x)
+        if required:
+            raise RuntimeError(f"peer-memory exchange unavailable on some rank (this rank: {why or 'ok'})")
+        import sys
+        print(f"[rank {rank}] peer-memory moment exchange unavailable ({why or 'another rank failed'}); using NCCL all-gather", file=sys.stderr)
+
+    def exchange_failed(self) -> bool:
+        """True if a peer-memory merge timed out waiting for a rank (synchronises the device)."""
+        return bool(self._xchg) and self.lib.qs_xchg_failed(self._xchg) != 0
+
+    def close(self) -> None:
+        if self._xchg:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)          # nobody unmaps while a peer may still store into the buffer
+            self.lib.qs_xchg_destroy(self._xchg)
+            self._xchg = None
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -114,6 +166,11 @@ class DeviceRunningMeanStd:
         if m is None:
             m = self._moments
         k = 1
+        if self._xchg:
+            rc = self.lib.qs_xchg_merge(self._xchg, C.c_void_p(self.stats.data_ptr()), C.c_void_p(m.data_ptr()), self._stream())
+            if rc != 0:
+                raise RuntimeError(f"qs_xchg_merge failed ({rc}): {self.lib.qs_xchg_last_error().decode()}")
+            return
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             k = dist.get_world_size(self.group)
             if self._gathered is None:
@@ -140,12 +197,12 @@ class DeviceVecNormalize:
     """
 
     def __init__(self, env, norm_obs: bool = True, norm_reward: bool = False, clip_obs: float = 10.0, clip_reward: float = 10.0,
-                 gamma: float = 0.99, epsilon: float = 1e-8, training: bool = True, group=None):
+                 gamma: float = 0.99, epsilon: float = 1e-8, training: bool = True, group=None, exchange: str = "auto"):
         self.env, self.norm_obs, self.norm_reward = env, norm_obs, norm_reward
         self.clip_obs, self.clip_reward, self.gamma, self.epsilon, self.training = clip_obs, clip_reward, gamma, epsilon, training
         dev, n, d = env.device, env.n_envs, env.obs_dim
-        self.obs_rms = DeviceRunningMeanStd(d, dev, group=group)
-        self.ret_rms = DeviceRunningMeanStd(1, dev, group=group)
+        self.obs_rms = DeviceRunningMeanStd(d, dev, group=group, exchange=exchange)
+        self.ret_rms = DeviceRunningMeanStd(1, dev, group=group, exchange=exchange)
         self.returns = torch.zeros(n, dtype=torch.float32, device=dev)
         self._ret_snapshot = torch.zeros(n, dtype=torch.float32, device=dev)
         self.norm_obs_buf = torch.empty((n, d), dtype=torch.float32, device=dev)

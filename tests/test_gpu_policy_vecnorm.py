@@ -205,3 +205,16 @@ def test_fused_obs_moments_in_step_kernel(variant, precision, n):
     env.step(a.float())
     np.testing.assert_array_equal(t2n(fused._moments), before)       # switched off: untouched
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node (run with gpurun --gpus 2)")
+def test_peer_memory_moment_exchange_matches_nccl_two_ranks():
+    """qs_xchg_merge (all-gather + Chan merge fused over NVLink peer memory) == NCCL all-gather + qs_vecnorm_merge, bit for bit,
+    on every rank, eagerly and from a CUDA graph (tools/peer_exchange_check.py under torchrun)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(root, "tools", "peer_exchange_check.py")], cwd=root, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "PEER_EXCHANGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

@@ -346,7 +346,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d_col, uint32_t a_col, int 
 // Also pulls the row this thread will need one tile later into L2.
 template <int OBS, bool PRECISE>
 __device__ __forceinline__ void stage_obs_row(const Args& p, int64_t e, bool live, int64_t tile_stride_rows, uint32_t x_addr,
-                                              const double* s_mean, const double* s_istd) {
+                                              const float* s_mean_hi, const float* s_mean_lo, const float* s_istd) {
     float x[K1];
 #pragma unroll
     for (int k = 0; k < K1; ++k) x[k] = 0.f;
@@ -371,7 +371,10 @@ __device__ __forceinline__ void stage_obs_row(const Args& p, int64_t e, bool liv
         if (p.norm) {
 #pragma unroll
             for (int k = 0; k < OBS; ++k) {
-                float v = (float)(((double)x[k] - s_mean[k]) * s_istd[k]);
+                // SB3 subtracts the float64 mean in float64.  Same result to ~2 float32 ulp without FP64 conversions (they run
+                // on the XU pipe this kernel is short of): mean = hi + lo in float32; x - hi is exact whenever x is within a
+                // factor 2 of the mean (Sterbenz), which is exactly the near-constant-column case that needs the digits.
+                const float v = __fmul_rn(__fadd_rn(__fadd_rn(x[k], -s_mean_hi[k]), -s_mean_lo[k]), s_istd[k]);
                 x[k] = fminf(fmaxf(v, -p.norm_clip), p.norm_clip);
             }
             if (p.obs_norm_out) {
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_tmem_base;
     __shared__ __align__(8) uint64_t s_bars[2];
-    __shared__ double s_mean[32], s_istd[32];
+    __shared__ float s_mean[32], s_mean_lo[32], s_istd[32];
     __shared__ __align__(16) float s_part[GROUPS][ROWS][NACT];                 // head partial sums of the second thread of each row
     constexpr int OFF_LO = W_SET;                                 // lo parts follow the hi parts
     constexpr int OFF_CONST = PRECISE ? 2 * W_SET : W_SET;
@@ -428,8 +431,9 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
             m = p.norm[1 + tid];
             is = 1.0 / sqrt(p.norm[1 + OBS + tid] + (double)p.norm_eps);
         }
-        s_mean[tid] = m;
-        s_istd[tid] = is;
+        s_mean[tid] = (float)m;
+        s_mean_lo[tid] = (float)(m - (double)(float)m);
+        s_istd[tid] = (float)is;
     }
     fence_async_smem();
     tc_fence_before();
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
         const int64_t tile = (int64_t)blockIdx.x * GROUPS + g;
         if (tile < n_tiles && half == 0) {
             const int64_t e = tile * ROWS + t;
-            stage_obs_row<OBS, PRECISE>(p, e, e < p.n, tile_stride * ROWS, lane_addr + COL_X, s_mean, s_istd);
+            stage_obs_row<OBS, PRECISE>(p, e, e < p.n, tile_stride * ROWS, lane_addr + COL_X, s_mean, s_mean_lo, s_istd);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
             }
             if (net == 1 && half == 0 && tile + tile_stride < n_tiles) {   // next tile's observations, under these MMAs
                 const int64_t en = (tile + tile_stride) * ROWS + t;
-                stage_obs_row<OBS, PRECISE>(p, en, en < p.n, tile_stride * ROWS, lane_addr + COL_X, s_mean, s_istd);
+                stage_obs_row<OBS, PRECISE>(p, en, en < p.n, tile_stride * ROWS, lane_addr + COL_X, s_mean, s_mean_lo, s_istd);
             }
             QS_TR();                                                    // b: issued
             __syncwarp();

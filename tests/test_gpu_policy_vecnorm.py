@@ -86,6 +86,7 @@ def test_policy_forward_with_fused_vecnormalize(golden_dir, impl):
     n = 10000
     g = torch.Generator(device="cuda").manual_seed(1)
     obs = torch.randn((n, 20), device="cuda", generator=g) * 3 + 1
+    obs[:, 6] = 1.0 - 1e-4 * torch.rand(n, device="cuda", generator=g)      # quaternion w near hover: mean ~1, std ~3e-5
     rms = DeviceRunningMeanStd(20, "cuda")
     rms.update(obs)
     normed = rms.normalize(obs)
@@ -93,7 +94,8 @@ def test_policy_forward_with_fused_vecnormalize(golden_dir, impl):
     a1, v1 = a1.clone(), v1.clone()
     out = torch.empty_like(obs)
     a2, v2, _ = pol.forward(obs, norm_stats=rms.stats, obs_norm_out=out)
-    assert torch.allclose(out, normed, atol=1e-6)
+    # fp32: float64 normalisation like SB3; tensor: float32 hi/lo mean split, within 2 float32 ulp of it (|z| < 8 here)
+    assert torch.allclose(out, normed, atol=1e-6 if impl == "fp32" else 2e-6)
     assert torch.allclose(a1, a2, atol=1e-4) and torch.allclose(v1, v2, atol=1e-2)
 
 

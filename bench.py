@@ -250,8 +250,10 @@ def run_gpu(args) -> None:
             # merge in one kernel over NVLink peer memory (qs_xchg_merge; NCCL all-gather + merge kernel if peers cannot be
             # mapped) -> normalisation fused into the policy kernel's obs load
             vn = DeviceRunningMeanStd(env.obs_dim, dev, exchange=args.vecnorm_exchange)
-            vn.attach(env)                                   # the step kernel reduces the obs it returns: no separate read pass
-            launches_per_step = 4                            # env step + moments_final + merge + policy forward
+            # the step kernel reduces the obs it returns (no separate read pass); on one GPU the kernel that finishes the
+            # moments also merges them into the running statistics, with several ranks the exchange kernel does
+            vn.attach(env, merge=(world == 1))
+            launches_per_step = 3 if world == 1 else 4       # env step + moments_final(+merge) [+ exchange/merge] + policy forward
     # uniform-random actions over the action box, pre-generated ring (step workload) / sampling noise (rollout)
     g = torch.Generator(device=dev).manual_seed(args.seed + rank)
     lo = torch.tensor([0.0, -1, -1, -1], device=dev)

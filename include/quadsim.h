@@ -142,6 +142,10 @@ int qs_step(qs_handle* h, const float* actions, float* obs_out, void* reward_out
  * summation offset (conditioning), or NULL.  moments_out == NULL switches the feature off.
  */
 int qs_step_moments(qs_handle* h, double* moments_out, const double* shift_stats);
+/* merge_stats != NULL: every qs_step additionally Chan-merges that batch triplet into the running statistics merge_stats
+ * (f64[1+2D]: count, mean, var), i.e. performs RunningMeanStd.update(obs) itself, in the kernel that finishes the moments --
+ * for a single-GPU rollout, where no exchange step sits between the two.  NULL (default) leaves the merge to the caller. */
+int qs_step_moments_merge(qs_handle* h, double* merge_stats);
 
 int qs_get_state(qs_handle* h, const qs_state_view* out, void* stream);
 int qs_set_state(qs_handle* h, const qs_state_view* in, void* stream);

@@ -126,7 +126,8 @@ class BatchedQuadEnv:
                                p(self.ep_return), p(self.ep_len), self._stream()), "qs_step")
         return StepOut(self.obs, self.reward, self.flags, self.terminal_obs, self.ep_return, self.ep_len)
 
-    def fuse_obs_moments(self, moments: torch.Tensor | None, shift_stats: torch.Tensor | None = None) -> None:
+    def fuse_obs_moments(self, moments: torch.Tensor | None, shift_stats: torch.Tensor | None = None,
+                         merge_stats: torch.Tensor | None = None) -> None:
         """From now on every step() also writes (n, mean[D], M2[D]) of the returned observations into `moments` (f64[1+2D]):
         the batch statistics VecNormalize needs, reduced inside the step kernel.  None switches it off.
         The kernel centres its sums on the mean already in `moments` (when its count is > 0), so seed it with the statistics
@@ -134,9 +135,14 @@ class BatchedQuadEnv:
         if moments is not None:
             assert moments.dtype == torch.float64 and moments.numel() == 1 + 2 * self.obs_dim and moments.device == self.device
             assert shift_stats is None or (shift_stats.dtype == torch.float64 and shift_stats.numel() == 1 + 2 * self.obs_dim)
-        self._mom_keep = (moments, shift_stats)
+        self._mom_keep = (moments, shift_stats, merge_stats)
         check(self.lib, self._h, self.lib.qs_step_moments(self._h, C.c_void_p(moments.data_ptr()) if moments is not None else None,
                                                           C.c_void_p(shift_stats.data_ptr()) if shift_stats is not None else None), "qs_step_moments")
+        # merge_stats (f64[1+2D] running count/mean/var): every step() also performs RunningMeanStd.update on it (single GPU)
+        if moments is not None:
+            assert merge_stats is None or (merge_stats.dtype == torch.float64 and merge_stats.numel() == 1 + 2 * self.obs_dim)
+            check(self.lib, self._h, self.lib.qs_step_moments_merge(self._h, C.c_void_p(merge_stats.data_ptr()) if merge_stats is not None else None),
+                  "qs_step_moments_merge")
 
     # -- state injection / extraction (parity tests, plotting façade) ------------------------------
     def get_state(self, fields=None) -> dict[str, torch.Tensor]:

@@ -83,7 +83,7 @@ __global__ void reset_uniforms_kernel(uint64_t seed, const int64_t* env_ids, con
 }
 
 template <typename Real, int VER>
-static size_t pool_bytes(int64_t n) { return (size_t)PoolLayout<Real, VER>::BYTES * (size_t)n; }
+static size_t pool_bytes(int64_t n) { return (size_t)PoolLayout<Real, VER>::TILE_BYTES * (size_t)((n + 31) / 32); }   // whole warp tiles
 
 static bool near_zero(double v) { return fabs(v) < 1e-300; }
 
@@ -161,7 +161,7 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     size_t bytes = 0;
     QS_DISPATCH(h, bytes = pool_bytes<Real, VER>(cfg->n_envs); h->bytes_per_env = PoolLayout<Real, VER>::BYTES;);
     h->pool_bytes = bytes;
-    err = cudaMalloc(&h->pool, bytes + 4096);   // slack: the TMA kernel rounds the last tile's tail-plane read up to 16 bytes
+    err = cudaMalloc(&h->pool, bytes + 4096);
     if (err != cudaSuccess) {
         set_error(nullptr, "qs_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
         delete h;
@@ -171,6 +171,7 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     h->mom_scratch = nullptr;
     h->mom_out = nullptr;
     h->mom_stats = nullptr;
+    h->mom_merge = nullptr;
     h->ls_tables = nullptr;
     h->ls_counters = nullptr;
     h->ls_steps = nullptr;
@@ -249,6 +250,14 @@ int qs_step_moments(qs_handle* h, double* moments_out, const double* shift_stats
     }
     h->mom_out = moments_out;
     h->mom_stats = moments_out ? shift_stats : nullptr;
+    if (!moments_out) h->mom_merge = nullptr;
+    return QS_OK;
+}
+
+int qs_step_moments_merge(qs_handle* h, double* merge_stats) {
+    if (!h) { set_error(nullptr, "qs_step_moments_merge: null handle"); return QS_EINVAL; }
+    if (merge_stats && !h->mom_out) { set_error(h, "qs_step_moments_merge: arm qs_step_moments first"); return QS_EINVAL; }
+    h->mom_merge = merge_stats;
     return QS_OK;
 }
 

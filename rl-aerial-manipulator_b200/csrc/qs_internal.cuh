@@ -12,6 +12,7 @@ struct qs_handle {
     double* mom_scratch;      // fused obs moments: per-CTA partials [grid][2*obs_dim]; null = off
     double* mom_out;          // caller-owned (n, mean[D], M2[D]) triplet
     const double* mom_stats;  // caller-owned VecNormalize stats used as the shift (or null)
+    double* mom_merge;        // caller-owned running statistics the batch triplet is merged into by the step (or null)
     qs::LsodaTables* ls_tables;
     int32_t* ls_counters;
     double* ls_steps;

@@ -380,7 +380,7 @@ __device__ __forceinline__ void stage_obs_row(const Args& p, int64_t e, bool liv
             if (p.obs_norm_out) {
                 float* orow = p.obs_norm_out + e * OBS;
 #pragma unroll
-                for (int k = 0; k < OBS; ++k) orow[k] = x[k];
+                for (int k = 0; k < OBS; ++k) __stcs(orow + k, x[k]);
             }
         }
 #pragma unroll
@@ -637,7 +637,8 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
             const float HALF_LOG_2PI = 0.9189385332046727f;
             const float lp = -0.5f * (eps.x * eps.x + eps.y * eps.y + eps.z * eps.z + eps.w * eps.w) - (ls[0] + ls[1] + ls[2] + ls[3]) -
                              4.0f * HALF_LOG_2PI;
-            reinterpret_cast<float4*>(p.actions)[e] = a;
+            __stcs(reinterpret_cast<float4*>(p.actions) + e, a);       // rollout-buffer outputs stream past L2; the clipped actions
+                                                                        // the env step reads next stay cacheable
             if (p.actions_clipped) {
                 float4 c;
                 c.x = fminf(fmaxf(a.x, p.lo[0]), p.hi[0]);
@@ -646,8 +647,8 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_tc_kernel(const Arg
                 c.w = fminf(fmaxf(a.w, p.lo[3]), p.hi[3]);
                 reinterpret_cast<float4*>(p.actions_clipped)[e] = c;
             }
-            p.values[e] = value;
-            p.logp[e] = lp;
+            __stcs(p.values + e, value);
+            __stcs(p.logp + e, lp);
         }
     }
     tc_fence_before();

@@ -1,10 +1,13 @@
 // qs_pool.cuh -- HBM layout of the hidden env state ("state pool") and its register pack/unpack.
 //
-// Layout: struct-of-arrays of 16-byte vectors.  The per-env record is SLOTS scalars of the kernel's
-// arithmetic type (the two 32-bit bookkeeping words are bit-cast into the last slot(s)); slot group v
-// (4 floats / 2 doubles) of env e lives at   base + (v * n_envs + e) * 16 bytes,
-// so a warp reads 512 contiguous bytes per LDG.128 and every plane is 16-byte aligned for any n_envs.
-// Left-over slots (SLOTS % vector width) follow as scalar planes.
+// Layout: tile-major array of struct-of-arrays tiles.  A tile is the record of one warp's 32 envs: the per-env record is SLOTS
+// scalars of the kernel's arithmetic type (the two 32-bit bookkeeping words are bit-cast into the last slot(s)); slot group v
+// (4 floats / 2 doubles) of the tile is a 512-byte plane (lane * 16), left-over slots (SLOTS % vector width) follow as scalar
+// planes (lane * sizeof(Real)):
+//     tile t of the pool at  base + t * TILE_BYTES,   plane v at + v * 512,   tail plane k at + NVEC * 512 + k * 32 * sizeof(Real)
+// so a warp reads and writes ONE contiguous, 128-byte aligned block per step (2688 B for v2/f32) with LDG.128/STG.128 that are
+// 512 contiguous bytes each -- every DRAM page the tile touches is used completely, where n-major planes ((v * n + e) * 16)
+// made each tile six separate 512-byte streams.  The pool is allocated for whole tiles; envs past n in the last tile are padding.
 //
 //   v2 f32: 13 state + 3 waypoint + final_yaw + last_distance + ep_return + 2 words = 21 slots = 84 B/env
 //   v2 f64: 19 doubles + 1 packed word pair                                         = 20 slots = 160 B/env
@@ -29,6 +32,8 @@ struct PoolLayout {
     static constexpr int NVEC = SLOTS / W;
     static constexpr int NTAIL = SLOTS % W;
     static constexpr int BYTES = SLOTS * (int)sizeof(Real);
+    static constexpr int TILE_BYTES = 32 * BYTES;                     // NVEC * 512 + NTAIL * 32 * sizeof(Real)
+    static constexpr int TAIL_OFF = NVEC * 512;
 };
 
 #if defined(__CUDACC__)
@@ -38,8 +43,8 @@ __device__ __forceinline__ uint32_t real_as_u32(float v) { return __float_as_uin
 template <typename Real, int VER>
 __device__ __forceinline__ void pool_unpack(const Real* slot, EnvState<Real, VER>& s);
 
-// One warp tile (32 envs) of the pool staged in shared memory by bulk copies: plane v at stage + v*512 (lane*16),
-// tail plane t at stage + NVEC*512 + t*128 (lane*4).  Conflict-free LDS.128 per plane.
+// One warp tile (32 envs) of the pool staged in shared memory by one bulk copy (same layout as in HBM): plane v at stage +
+// v*512 (lane*16), tail plane t at stage + NVEC*512 + t*128 (lane*4).  Conflict-free LDS.128 per plane.
 template <typename Real, int VER>
 __device__ __forceinline__ void pool_load_staged(const unsigned char* stage, int lane, EnvState<Real, VER>& s) {
     using L = PoolLayout<Real, VER>;
@@ -67,10 +72,13 @@ __device__ __forceinline__ void pool_load(const void* __restrict__ base, int64_t
     using L = PoolLayout<Real, VER>;
     using V = typename VecOf<Real>::type;
     Real slot[L::NVEC * L::W + (L::NTAIL ? L::NTAIL : 1)];
-    const V* vb = reinterpret_cast<const V*>(base);
+    (void)n;
+    const unsigned char* tb0 = reinterpret_cast<const unsigned char*>(base) + (e >> 5) * (int64_t)L::TILE_BYTES;
+    const int ln = (int)(e & 31);
+    const V* vb = reinterpret_cast<const V*>(tb0) + ln;
 #pragma unroll
     for (int v = 0; v < L::NVEC; ++v) {
-        const V x = __ldg(vb + (int64_t)v * n + e);
+        const V x = __ldg(vb + v * 32);
         if (L::W == 4) {
             const float4 f = *reinterpret_cast<const float4*>(&x);
             slot[4 * v + 0] = (Real)f.x; slot[4 * v + 1] = (Real)f.y; slot[4 * v + 2] = (Real)f.z; slot[4 * v + 3] = (Real)f.w;
@@ -79,9 +87,9 @@ __device__ __forceinline__ void pool_load(const void* __restrict__ base, int64_t
             slot[2 * v + 0] = (Real)f.x; slot[2 * v + 1] = (Real)f.y;
         }
     }
-    const Real* tb = reinterpret_cast<const Real*>(vb + (int64_t)L::NVEC * n);
+    const Real* tb = reinterpret_cast<const Real*>(tb0 + L::TAIL_OFF) + ln;
 #pragma unroll
-    for (int t = 0; t < L::NTAIL; ++t) slot[L::NVEC * L::W + t] = __ldg(tb + (int64_t)t * n + e);
+    for (int t = 0; t < L::NTAIL; ++t) slot[L::NVEC * L::W + t] = __ldg(tb + t * 32);
     pool_unpack<Real, VER>(slot, s);
 }
 
@@ -125,7 +133,10 @@ __device__ __forceinline__ void pool_store(void* __restrict__ base, int64_t n, i
     } else {
         slot[k] = (Real)__longlong_as_double((long long)(((unsigned long long)s.episode << 32) | (unsigned long long)s.bits));
     }
-    V* vb = reinterpret_cast<V*>(base);
+    (void)n;
+    unsigned char* tb0 = reinterpret_cast<unsigned char*>(base) + (e >> 5) * (int64_t)L::TILE_BYTES;
+    const int ln = (int)(e & 31);
+    V* vb = reinterpret_cast<V*>(tb0) + ln;
 #pragma unroll
     for (int v = 0; v < L::NVEC; ++v) {
         V x;
@@ -136,11 +147,11 @@ __device__ __forceinline__ void pool_store(void* __restrict__ base, int64_t n, i
             double2 f = make_double2((double)slot[2 * v], (double)slot[2 * v + 1]);
             x = *reinterpret_cast<V*>(&f);
         }
-        vb[(int64_t)v * n + e] = x;
+        vb[v * 32] = x;
     }
-    Real* tb = reinterpret_cast<Real*>(vb + (int64_t)L::NVEC * n);
+    Real* tb = reinterpret_cast<Real*>(tb0 + L::TAIL_OFF) + ln;
 #pragma unroll
-    for (int t = 0; t < L::NTAIL; ++t) tb[(int64_t)t * n + e] = slot[L::NVEC * L::W + t];
+    for (int t = 0; t < L::NTAIL; ++t) tb[t * 32] = slot[L::NVEC * L::W + t];
 }
 #endif  // __CUDACC__
 

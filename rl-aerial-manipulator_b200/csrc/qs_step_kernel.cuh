@@ -279,15 +279,11 @@ __device__ __forceinline__ void tma_request(const StepParams<float>& p, int64_t 
     const int64_t e0 = wt * 32;
     const int64_t rem = p.n - e0;
     const uint32_t rows = rem < 32 ? (uint32_t)rem : 32u;
-    const uint32_t vbytes = rows * 16u, tbytes = (rows * 4u + 15u) & ~15u;     // the pool is padded: a rounded-up tail read stays inside it
+    const uint32_t vbytes = rows * 16u;
     const uint32_t b = smem_addr(bar), d = smem_addr(stage);
-    mbar_expect_tx(b, (uint32_t)(L::NVEC + 1) * vbytes + (uint32_t)L::NTAIL * tbytes);
+    mbar_expect_tx(b, (uint32_t)L::TILE_BYTES + vbytes);
     const unsigned char* base = reinterpret_cast<const unsigned char*>(p.pool);
-#pragma unroll
-    for (int v = 0; v < L::NVEC; ++v) bulk_g2s(d + v * 512, base + ((int64_t)v * p.n + e0) * 16, vbytes, b);
-#pragma unroll
-    for (int t = 0; t < L::NTAIL; ++t)
-        bulk_g2s(d + L::NVEC * 512 + t * 128, base + (int64_t)L::NVEC * p.n * 16 + ((int64_t)t * p.n + e0) * 4, tbytes, b);
+    bulk_g2s(d, base + wt * (int64_t)L::TILE_BYTES, (uint32_t)L::TILE_BYTES, b);     // the whole tile record is one contiguous block
     bulk_g2s(d + TmaStage<VER>::ACT_OFF, p.actions + e0 * 4, vbytes, b);
 }
 

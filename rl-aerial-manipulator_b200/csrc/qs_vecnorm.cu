@@ -61,33 +61,65 @@ __global__ void moments_partial_kernel(const float* __restrict__ x, int64_t n, i
     }
 }
 
-// Fixed-order sum of the CTA partials: 1024 threads = 16 slices x 64 columns (2d <= 64); each slice adds its share of the
-// partials in block order, then the 16 slice sums are added in slice order -> deterministic, ~2 us instead of a 100 us
-// single-thread chain.
+// Fixed-order sum of the CTA partials: 1024 threads = S slices x 2d columns (S = 1024 / 2d, 25 for d = 20); each slice adds its
+// share of the partials in block order (loads unrolled so they overlap), then the slice sums are added in slice order ->
+// deterministic, ~2 us instead of a 100 us single-thread chain.
 // shift: per-column offset the partial sums were taken around -- row 0 of x (qs_batch_moments) or the running mean
 // stats[1..d] (fused moments of the env-step kernel; x == nullptr), or zero when both are null.
+// merge != nullptr: the batch triplet is also Chan-merged into the running statistics `merge` (RunningMeanStd.update), same
+// arithmetic as vecnorm_merge_kernel with k = 1.
 __global__ void __launch_bounds__(1024) moments_final_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                              const double* __restrict__ partial, int blocks, int64_t n, int d,
-                                                             double* __restrict__ out /*[1+2d]*/) {
-    __shared__ double s[16][64];
-    const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
+                                                             double* __restrict__ out /*[1+2d]*/, double* merge) {
+    __shared__ double s[64][64];
+    const int w = 2 * d, S = (1024 / w) < 64 ? (1024 / w) : 64;
+    const int col = threadIdx.x % w, slice = threadIdx.x / w;
     // fused path (x == nullptr): same offset rule as env_step_kernel -- the previous triplet's mean if it has one.  Read it
     // before the barrier below; the triplet is overwritten after it.
     double shift = 0.0;
     if (threadIdx.x < d) shift = x ? (double)x[threadIdx.x] : (out[0] > 0.0 ? out[1 + threadIdx.x] : (stats ? stats[1 + threadIdx.x] : 0.0));
-    double acc = 0.0;
-    if (col < 2 * d)
-        for (int b = slice; b < blocks; b += 16) acc += partial[(int64_t)b * 2 * d + col];
-    s[slice][col] = acc;
+    if (slice < S) {
+        double acc = 0.0;
+        int b = slice;
+        for (; b + 3 * S < blocks; b += 4 * S) {
+            const double v0 = partial[(int64_t)b * w + col], v1 = partial[(int64_t)(b + S) * w + col];
+            const double v2 = partial[(int64_t)(b + 2 * S) * w + col], v3 = partial[(int64_t)(b + 3 * S) * w + col];
+            acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; b < blocks; b += S) acc += partial[(int64_t)b * w + col];
+        s[slice][col] = acc;
+    }
     __syncthreads();
+    double mean_b = 0.0, m2_b = 0.0;
+    const double cnt = (double)n;
     if (threadIdx.x < d) {
         const int c = threadIdx.x;
         double s1 = 0.0, s2 = 0.0;
-        for (int k = 0; k < 16; ++k) { s1 += s[k][c]; s2 += s[k][d + c]; }
-        const double cnt = (double)n;
-        out[1 + c] = shift + s1 / cnt;               // batch mean
-        out[1 + d + c] = s2 - s1 * s1 / cnt;         // batch M2 = sum (x - mean)^2
+        for (int k = 0; k < S; ++k) { s1 += s[k][c]; s2 += s[k][d + c]; }
+        mean_b = shift + s1 / cnt;                   // batch mean
+        m2_b = s2 - s1 * s1 / cnt;                   // batch M2 = sum (x - mean)^2
+        out[1 + c] = mean_b;
+        out[1 + d + c] = m2_b;
         if (c == 0) out[0] = cnt;
+    }
+    if (merge) {
+        double count = 0.0, mean = 0.0, var = 0.0;
+        if (threadIdx.x < d) {
+            const int c = threadIdx.x;
+            count = merge[0]; mean = merge[1 + c]; var = merge[1 + d + c];
+            const double delta = mean_b - mean;
+            const double tot = count + cnt;
+            mean = mean + delta * cnt / tot;
+            const double M2 = var * count + m2_b + delta * delta * count * cnt / tot;
+            var = M2 / tot;
+            count = tot;
+        }
+        __syncthreads();                              // every column has read merge[0] before it is rewritten
+        if (threadIdx.x < d) {
+            merge[1 + threadIdx.x] = mean;
+            merge[1 + d + threadIdx.x] = var;
+            if (threadIdx.x == 0) merge[0] = count;
+        }
     }
 }
 
@@ -168,7 +200,7 @@ static int vn_check(cudaError_t err, const char* what) {
 
 int launch_moments_final(qs_handle* h, unsigned blocks, cudaStream_t st) {
     const int d = h->cfg.env_version == 2 ? 20 : 17;
-    moments_final_kernel<<<1, 1024, 0, st>>>(nullptr, h->mom_stats, h->mom_scratch, (int)blocks, h->cfg.n_envs, d, h->mom_out);
+    moments_final_kernel<<<1, 1024, 0, st>>>(nullptr, h->mom_stats, h->mom_scratch, (int)blocks, h->cfg.n_envs, d, h->mom_out, h->mom_merge);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error(h, "moments_final_kernel launch failed: %s", cudaGetErrorString(err));
@@ -198,7 +230,7 @@ int qs_batch_moments(const float* x, int64_t n, int d, double* moments_out, doub
     if (blocks > MOM_MAX_BLOCKS) blocks = MOM_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
     moments_partial_kernel<<<(unsigned)blocks, bd, 2 * bd * sizeof(double), (cudaStream_t)stream>>>(x, n, d, scratch);
-    moments_final_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, nullptr, scratch, (int)blocks, n, d, moments_out);
+    moments_final_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, nullptr, scratch, (int)blocks, n, d, moments_out, nullptr);
     return vn_check(cudaGetLastError(), "qs_batch_moments");
 }
 

@@ -154,16 +154,22 @@ class DeviceRunningMeanStd:
         """RunningMeanStd.update(x) for the batch sharded over all ranks of `group` (or this GPU alone)."""
         self.update_from_moments(self.batch_moments(x))
 
-    def attach(self, env) -> None:
+    def attach(self, env, merge: bool = False) -> None:
         """Let `env`'s step kernel produce the batch moments of the observations it returns (no separate read pass):
-        after every env.step(), call update_from_moments()."""
+        after every env.step(), call update_from_moments().  merge=True (single GPU only): the step also merges them into
+        these running statistics itself (qs_step_moments_merge) and update_from_moments() without argument becomes a no-op."""
+        if merge and self._gathered is not None:
+            raise ValueError("merge=True needs a single rank: with several ranks the moments are exchanged before the merge")
         self.batch_moments(env.obs)                     # seeds the summation offset with the current observations' mean
-        env.fuse_obs_moments(self._moments, self.stats)
+        env.fuse_obs_moments(self._moments, self.stats, merge_stats=self.stats if merge else None)
+        self.env_merges = bool(merge)
 
     def update_from_moments(self, m: torch.Tensor | None = None) -> None:
         """Merge a batch triplet (n, mean, M2) -- by default `self._moments`, e.g. filled by the env-step kernel
         (BatchedQuadEnv.fuse_obs_moments) -- into the running statistics, all-gathering over the ranks first."""
         if m is None:
+            if getattr(self, "env_merges", False):
+                return                                  # the env step already merged its batch (attach(merge=True))
             m = self._moments
         k = 1
         if self._xchg:

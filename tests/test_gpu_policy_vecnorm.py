@@ -220,3 +220,26 @@ def test_peer_memory_moment_exchange_matches_nccl_two_ranks():
                         "--master-port", "29517", os.path.join(root, "tools", "peer_exchange_check.py")], cwd=root, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "PEER_EXCHANGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.gpu
+def test_step_kernel_merges_running_statistics_itself():
+    """attach(env, merge=True): RunningMeanStd.update happens inside qs_step (the kernel that finishes the moments); the running
+    statistics must equal, bit for bit, those of the two-launch path (moments triplet -> qs_vecnorm_merge) on the same env."""
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd
+    stats = {}
+    for merge in (False, True):
+        env = BatchedQuadEnv(20000, env_version=2, precision="f32", seed=9)
+        rms = DeviceRunningMeanStd(env.obs_dim, "cuda")
+        env.reset()
+        rms.attach(env, merge=merge)
+        g = torch.Generator(device="cuda").manual_seed(4)
+        for t in range(25):
+            a = torch.rand((20000, 4), device="cuda", generator=g) * torch.tensor([1.0, 2, 2, 2], device="cuda") - torch.tensor([0, 1, 1, 1.0], device="cuda")
+            env.step(a)
+            rms.update_from_moments()                      # no-op when the env merges
+        stats[merge] = t2n(rms.stats).copy()
+        assert abs(stats[merge][0] - (1e-4 + 25 * 20000)) < 1e-6
+        env.close()
+    np.testing.assert_array_equal(stats[True], stats[False])

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 1
+#define QS_ABI_VERSION 2
 
 /* error codes */
 #define QS_OK 0
@@ -51,6 +51,7 @@ extern "C" {
 #define QS_ACT_DIM 4
 #define QS_STATE_DIM 13
 #define QS_MAX_WAYPOINTS 3
+#define QS_TRIG_TAB 6
 #define QS_RESET_UNIFORMS 16
 
 typedef struct qs_handle qs_handle;
@@ -71,7 +72,9 @@ typedef struct qs_config {
     int32_t action_scale_f32;  /* 1: scale actions in float32 like NumPy>=2 does for float32 actions (default) */
     int32_t auto_reset;        /* 1: DummyVecEnv semantics, done envs are reset inside the step kernel */
     int32_t device;            /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t v2_random_waypoints; /* env_version 2 only.  0: num_waypoints = 1, as shipped (rl_env_scaledObs.py:47).
+                                    1: num_waypoints = np.random.randint(2, 4), the alternative the reference keeps commented
+                                    out at :46 (drawn at that position), trajectories of 2-3 waypoints */
     int64_t n_envs;            /* envs owned by this handle (this rank's shard) */
     int64_t env_id_offset;     /* global id of local env 0; Philox is keyed on the global id, so a batch sharded
                                   over G ranks draws the same episodes as the unsharded batch */
@@ -82,7 +85,8 @@ typedef struct qs_config {
     double inertia[9], inv_inertia[9];
     double mix[16], inv_mix[16];
     double max_prop_thrust, min_prop_thrust; /* maxF/4, minF/4 */
-    double sin_tab[QS_MAX_WAYPOINTS], cos_tab[QS_MAX_WAYPOINTS]; /* sin/cos(2*pi*j/K), j=1..K (utils2/utils.py:41,84-85) */
+    double sin_tab[QS_TRIG_TAB], cos_tab[QS_TRIG_TAB]; /* np.sin / np.cos of 2*pi*j/K for K = 1..3, j = 1..K at index
+                                                          K*(K-1)/2 + j-1 (utils2/utils.py:41,84-85) */
     double lsoda_rtol, lsoda_atol;           /* odeint defaults: 1.49012e-8 */
 } qs_config;
 
@@ -150,7 +154,8 @@ int qs_step_moments_merge(qs_handle* h, double* merge_stats);
 int qs_get_state(qs_handle* h, const qs_state_view* out, void* stream);
 int qs_set_state(qs_handle* h, const qs_state_view* in, void* stream);
 
-/* The QS_RESET_UNIFORMS unit uniforms the reset of (global env id, episode) consumes: f64[n,16]. Test hook. */
+/* The unit uniforms the reset of (global env id, episode) may consume: f64[n,QS_RESET_UNIFORMS]. Test hook. */
+#define QS_RESET_UNIFORMS 18
 int qs_reset_uniforms(qs_handle* h, const int64_t* env_ids, const int32_t* episodes, int64_t n, double* out,
                       void* stream);
 

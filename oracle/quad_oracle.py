@@ -57,7 +57,7 @@ INFO_STOPPED = 2
 INFO_CRASHED = 4
 INFO_OOB = 8
 
-N_UNIFORMS = 16  # unit uniforms one reset may consume (v2 uses <= 15, v1 <= 11)
+N_UNIFORMS = 18  # unit uniforms one reset may consume (v2 <= 16, v2 with a drawn waypoint count 17, v1 <= 11)
 
 OBS_DIM = {"v1": 17, "v1_raw": 17, "v2": 20}
 MAX_STEPS = {"v1": 1200, "v1_raw": 1200, "v2": 2000}
@@ -343,11 +343,13 @@ def reset_env(b: EnvBatch, i: int, rng) -> None:
     b.last_distance[i] = np.nan
     b.wp_list[i] = 0.0
     if b.version == "v2":
+        nw = 1  # num_waypoints = 1 (:47)
+        if getattr(b, "v2_random_waypoints", False):
+            nw = int(rng.randint(2, 4))  # the alternative kept commented out at :46, drawn at that position
         uni(-np.pi / 2, np.pi / 2), uni(-np.pi / 2, np.pi / 2), uni(-np.pi, np.pi)  # unused attitude draws
         rng.rand()  # `rand() < 0`: never true
         b.counter[i] = 0
         b.final_reached[i] = False
-        nw = 1  # num_waypoints = 1 (:47)
         if rng.rand() < 0.3:
             kind = 0
         elif rng.rand() < 0.6:
@@ -568,8 +570,9 @@ class VecOracle:
     path and this oracle can be driven by the very same Philox stream.
     """
 
-    def __init__(self, version, n, uniforms, integrator="lsoda", substeps=1, action_f32=True, max_wp=None):
-        self.b = EnvBatch.empty(version, n, max_wp)
+    def __init__(self, version, n, uniforms, integrator="lsoda", substeps=1, action_f32=True, max_wp=None, v2_random_waypoints=False):
+        self.b = EnvBatch.empty(version, n, 3 if v2_random_waypoints else max_wp)
+        self.b.v2_random_waypoints = bool(v2_random_waypoints)     # rl_env_scaledObs.py:46 alternative (see reset_env)
         self.uniforms = uniforms
         self.integrator, self.substeps, self.action_f32 = integrator, substeps, action_f32
         self.ep_return = np.zeros(n)

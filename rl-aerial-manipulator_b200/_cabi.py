@@ -16,26 +16,27 @@ from . import params
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QS_LIB_PATH") or os.path.join(HERE, "lib", "libquadsim.so")
 
-QS_ABI_VERSION = 1
+QS_ABI_VERSION = 2
 QS_F32, QS_F64 = 0, 1
 QS_RK4, QS_LSODA = 0, 1
 FLAG_TERMINATED, FLAG_TRUNCATED, FLAG_SUCCESS, FLAG_STOPPED = 0x01, 0x02, 0x04, 0x08
 FLAG_CRASHED, FLAG_OOB, FLAG_LSODA_FAIL = 0x10, 0x20, 0x80
 MAX_WAYPOINTS = 3
-RESET_UNIFORMS = 16
+RESET_UNIFORMS = 18
+TRIG_TAB = 6
 
 
 class QsConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("env_version", C.c_int32), ("obs_scaled", C.c_int32), ("precision", C.c_int32),
         ("integrator", C.c_int32), ("substeps", C.c_int32), ("action_scale_f32", C.c_int32), ("auto_reset", C.c_int32),
-        ("device", C.c_int32), ("reserved", C.c_int32),
+        ("device", C.c_int32), ("v2_random_waypoints", C.c_int32),
         ("n_envs", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
         ("mass", C.c_double), ("g", C.c_double), ("dt", C.c_double),
         ("inertia", C.c_double * 9), ("inv_inertia", C.c_double * 9),
         ("mix", C.c_double * 16), ("inv_mix", C.c_double * 16),
         ("max_prop_thrust", C.c_double), ("min_prop_thrust", C.c_double),
-        ("sin_tab", C.c_double * 3), ("cos_tab", C.c_double * 3),
+        ("sin_tab", C.c_double * TRIG_TAB), ("cos_tab", C.c_double * TRIG_TAB),
         ("lsoda_rtol", C.c_double), ("lsoda_atol", C.c_double),
     ]
 
@@ -47,7 +48,7 @@ class QsStateView(C.Structure):
 
 
 def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", substeps=1, obs_scaled=True,
-                action_scale_f32=True, auto_reset=True, device=0, env_id_offset=0, seed=0) -> QsConfig:
+                action_scale_f32=True, auto_reset=True, device=0, env_id_offset=0, seed=0, v2_random_waypoints=False) -> QsConfig:
     """qs_config with the reference's model constants (params.py) and NumPy-evaluated trig tables."""
     c = QsConfig()
     c.abi_version = QS_ABI_VERSION
@@ -58,6 +59,7 @@ def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", subs
     c.substeps = int(substeps)
     c.action_scale_f32 = int(bool(action_scale_f32))
     c.auto_reset = int(bool(auto_reset))
+    c.v2_random_waypoints = int(bool(v2_random_waypoints))
     c.device = int(device)
     c.n_envs = int(n_envs)
     c.env_id_offset = int(env_id_offset)
@@ -69,11 +71,14 @@ def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", subs
     c.inv_mix[:] = params.invA.reshape(-1).tolist()
     c.max_prop_thrust = params.maxF / 4
     c.min_prop_thrust = params.minF / 4
-    k = 1  # waypoints per v2 trajectory (rl_env_scaledObs.py:47); the tables hold sin/cos(2*pi*j/k)
-    for j in range(1, 4):
-        t = min(j, k) / k
-        c.sin_tab[j - 1] = float(np.sin(2 * t * np.pi))
-        c.cos_tab[j - 1] = float(np.cos(2 * np.pi * 1 * t))
+    # v2 trajectory generators (utils2/utils.py:41,84-85): sin(2*t*pi), t = j/K, and cos/sin((j/K) * 2*pi*turns), turns = 1, evaluated
+    # with the reference's own NumPy expressions for K = 1 (as shipped, rl_env_scaledObs.py:47) and K = 2, 3 (the :46 alternative)
+    for k in (1, 2, 3):
+        for j in range(1, k + 1):
+            t = j / k
+            c.sin_tab[k * (k - 1) // 2 + j - 1] = float(np.sin(2 * t * np.pi))
+            c.cos_tab[k * (k - 1) // 2 + j - 1] = float(np.cos((j / k) * (2 * np.pi * 1)))
+            assert np.sin(2 * t * np.pi) == np.sin((j / k) * (2 * np.pi * 1))     # one angle per (K, j): the helix shares the sine
     c.lsoda_rtol = c.lsoda_atol = params.ODEINT_TOL
     return c
 

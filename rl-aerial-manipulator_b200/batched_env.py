@@ -53,11 +53,15 @@ class StepOut:
 
 
 class BatchedQuadEnv:
-    """N independent WaypointQuadEnv instances stepped by one fused sm_100a kernel."""
+    """N independent WaypointQuadEnv instances stepped by one fused sm_100a kernel.
+
+    v2_random_waypoints (env_version 2): False = `num_waypoints = 1` as the reference ships it (rl_env_scaledObs.py:47); True = the
+    `np.random.randint(2, 4)` alternative it keeps commented out at :46 -- trajectories of 2 or 3 waypoints."""
 
     def __init__(self, n_envs: int, env_version: int = 2, precision: str = "f32", integrator: str = "rk4",
                  substeps: int = 1, obs_scaled: bool = True, action_scale_f32: bool = True, auto_reset: bool = True,
-                 device: int | torch.device | None = None, env_id_offset: int = 0, seed: int = 0):
+                 device: int | torch.device | None = None, env_id_offset: int = 0, seed: int = 0,
+                 v2_random_waypoints: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedQuadEnv needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         if device is None:
@@ -66,7 +70,8 @@ class BatchedQuadEnv:
         self.lib = load_library()
         self.cfg = make_config(env_version=env_version, n_envs=n_envs, precision=precision, integrator=integrator,
                                substeps=substeps, obs_scaled=obs_scaled, action_scale_f32=action_scale_f32,
-                               auto_reset=auto_reset, device=self.device.index, env_id_offset=env_id_offset, seed=seed)
+                               auto_reset=auto_reset, device=self.device.index, env_id_offset=env_id_offset, seed=seed,
+                               v2_random_waypoints=v2_random_waypoints)
         self.n_envs = int(n_envs)
         self.env_version = int(env_version)
         self.obs_dim = OBS_DIM[self.env_version]
@@ -168,10 +173,10 @@ class BatchedQuadEnv:
         torch.cuda.current_stream(self.device).synchronize()  # `keep` must outlive the kernel
 
     def reset_uniforms(self, env_ids: torch.Tensor, episodes: torch.Tensor) -> torch.Tensor:
-        """The 16 unit uniforms the reset of (global env id, episode) consumes -- test hook."""
+        """The RESET_UNIFORMS unit uniforms the reset of (global env id, episode) may consume -- test hook."""
         env_ids = env_ids.to(device=self.device, dtype=torch.int64).contiguous()
         episodes = episodes.to(device=self.device, dtype=torch.int32).contiguous()
-        out = torch.empty((env_ids.numel(), 16), dtype=torch.float64, device=self.device)
+        out = torch.empty((env_ids.numel(), _cabi.RESET_UNIFORMS), dtype=torch.float64, device=self.device)
         check(self.lib, self._h, self.lib.qs_reset_uniforms(self._h, C.c_void_p(env_ids.data_ptr()), C.c_void_p(episodes.data_ptr()),
                                                            env_ids.numel(), C.c_void_p(out.data_ptr()), self._stream()), "qs_reset_uniforms")
         return out

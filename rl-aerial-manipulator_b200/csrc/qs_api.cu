@@ -77,9 +77,9 @@ __global__ void set_state_kernel(void* pool, int64_t n, qs_state_view v) {
 __global__ void reset_uniforms_kernel(uint64_t seed, const int64_t* env_ids, const int32_t* episodes, int64_t n, double* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double u[16];
+    double u[QS_N_UNIFORMS];
     reset_uniforms(seed, (uint64_t)env_ids[i], (uint32_t)episodes[i], u);
-    for (int k = 0; k < 16; ++k) out[i * 16 + k] = u[k];
+    for (int k = 0; k < QS_N_UNIFORMS; ++k) out[i * QS_N_UNIFORMS + k] = u[k];
 }
 
 template <typename Real, int VER>
@@ -101,15 +101,15 @@ using namespace qs;
     } while (0)
 
 // dispatch on (precision, env_version): BODY sees `Real` and `VER`
-#define QS_DISPATCH(h, ...)                                                                   \
-    do {                                                                                      \
-        if ((h)->cfg.precision == QS_F32) {                                                   \
-            using Real = float;                                                               \
-            if ((h)->cfg.env_version == 2) { constexpr int VER = ENV_V2; __VA_ARGS__ } else { constexpr int VER = ENV_V1; __VA_ARGS__ } \
-        } else {                                                                              \
-            using Real = double;                                                              \
-            if ((h)->cfg.env_version == 2) { constexpr int VER = ENV_V2; __VA_ARGS__ } else { constexpr int VER = ENV_V1; __VA_ARGS__ } \
-        }                                                                                     \
+#define QS_DISPATCH(h, ...)                                     \
+    do {                                                        \
+        if ((h)->cfg.precision == QS_F32) {                     \
+            using Real = float;                                 \
+            QS_FOR_VARIANT(h, __VA_ARGS__);                     \
+        } else {                                                \
+            using Real = double;                                \
+            QS_FOR_VARIANT(h, __VA_ARGS__);                     \
+        }                                                       \
     } while (0)
 
 extern "C" {
@@ -128,6 +128,7 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     if (cfg->integrator == QS_LSODA && cfg->precision != QS_F64) { set_error(nullptr, "qs_create: QS_LSODA requires QS_F64"); return QS_EINVAL; }
     if (cfg->integrator == QS_RK4 && cfg->substeps < 1) { set_error(nullptr, "qs_create: substeps must be >= 1"); return QS_EINVAL; }
     if (cfg->n_envs < 1) { set_error(nullptr, "qs_create: n_envs must be >= 1"); return QS_EINVAL; }
+    if (cfg->v2_random_waypoints && cfg->env_version != 2) { set_error(nullptr, "qs_create: v2_random_waypoints needs env_version 2"); return QS_EINVAL; }
     if (cfg->env_version == 2 && !cfg->obs_scaled) { set_error(nullptr, "qs_create: v2 has no raw-observation variant"); return QS_EINVAL; }
     const int zero_idx[4] = {1, 3, 5, 7};
     for (int k = 0; k < 4; ++k)
@@ -216,7 +217,7 @@ int qs_reset(qs_handle* h, const uint8_t* env_mask, float* obs_out, void* stream
     const int64_t n = h->cfg.n_envs;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     ResetConsts rc;
-    for (int i = 0; i < 3; ++i) { rc.sin_tab[i] = h->cfg.sin_tab[i]; rc.cos_tab[i] = h->cfg.cos_tab[i]; }
+    for (int i = 0; i < QS_TRIG_TAB; ++i) { rc.sin_tab[i] = h->cfg.sin_tab[i]; rc.cos_tab[i] = h->cfg.cos_tab[i]; }
     QS_DISPATCH(h, (env_reset_kernel<Real, VER><<<blocks, 256, 0, st>>>(h->pool, n, env_mask, obs_out, h->cfg.obs_scaled, h->cfg.seed,
                                                                         h->cfg.env_id_offset, rc, h->initialized ? 0 : 1)););
     QS_CUDA(h, cudaGetLastError());

@@ -12,7 +12,10 @@
 
 namespace qs {
 
-enum : int { ENV_V1 = 1, ENV_V2 = 2 };
+// ENV_V2M: v2 with waypoint lists of 2-3 entries (the `randint(2, 4)` alternative of rl_env_scaledObs.py:46); same step logic and
+// observation as ENV_V2, a wider state record
+enum : int { ENV_V1 = 1, ENV_V2 = 2, ENV_V2M = 3 };
+QS_HD constexpr bool is_v2(int ver) { return ver == ENV_V2 || ver == ENV_V2M; }
 
 constexpr uint32_t FLAG_TERMINATED = 0x01, FLAG_TRUNCATED = 0x02, FLAG_SUCCESS = 0x04, FLAG_STOPPED = 0x08,
                    FLAG_CRASHED = 0x10, FLAG_OOB = 0x20, FLAG_LSODA_FAIL = 0x80;
@@ -20,11 +23,12 @@ constexpr uint32_t FLAG_TERMINATED = 0x01, FLAG_TRUNCATED = 0x02, FLAG_SUCCESS =
 template <int VER> struct EnvTraits;
 template <> struct EnvTraits<ENV_V1> { static constexpr int NWP = 2, OBS = 17, MAX_STEPS = 1200; };
 template <> struct EnvTraits<ENV_V2> { static constexpr int NWP = 1, OBS = 20, MAX_STEPS = 2000; };
+template <> struct EnvTraits<ENV_V2M> { static constexpr int NWP = 3, OBS = 20, MAX_STEPS = 2000; };
 constexpr int COUNTER_LIMIT = 500;
 
 // Constants of the episode generator that must be bit-identical to NumPy's (sin/cos of 2*pi*j/K).
 struct ResetConsts {
-    double sin_tab[3], cos_tab[3];
+    double sin_tab[6], cos_tab[6];   // index K*(K-1)/2 + j-1 for K = 1..3, j = 1..K
 };
 
 // Hidden state of one env, held in registers for the whole step.
@@ -151,7 +155,7 @@ QS_HD void make_obs(const EnvState<Real, VER>& s, int obs_scaled, float* obs) {
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) obs[6 + i] = (float)s.y[6 + i];
-    if (VER == ENV_V2) {
+    if (is_v2(VER)) {
         // rel_pos_next = list[index+1] - current_waypoint while index < len-1, else zeros (:104-107)
         Real nx[3] = {Real(0), Real(0), Real(0)};
         const int idx = s.wp_index(), n = s.n_wp();
@@ -199,7 +203,7 @@ QS_HD uint32_t step_logic(EnvState<Real, VER>& s, Real& reward_out, int& ep_len)
     const bool fin0 = fin;
 
     // _calculate_reward (v2 :198-231, v1 :142-168)
-    Real dist_r = -d * (VER == ENV_V2 ? Real(10) : Real(2));
+    Real dist_r = -d * (is_v2(VER) ? Real(10) : Real(2));
     Real speed = Real(-0.1) * (vn * vn);
     if (wn > Real(0.1)) speed -= Real(0.01) * (wn * wn);
     Real time_pen = Real(-0.1);
@@ -209,7 +213,7 @@ QS_HD uint32_t step_logic(EnvState<Real, VER>& s, Real& reward_out, int& ep_len)
         if (prog > Real(0)) prog += Real(2);
     }
     s.last_d = d;
-    if (VER == ENV_V2 && fin0) {
+    if (is_v2(VER) && fin0) {
         prog = Real(0);
         time_pen = Real(0);
         if (d < Real(0.1)) dist_r = Real(1);
@@ -220,7 +224,7 @@ QS_HD uint32_t step_logic(EnvState<Real, VER>& s, Real& reward_out, int& ep_len)
     bool early = false;
     bool truncated;
 
-    if (VER == ENV_V2) {
+    if (is_v2(VER)) {
         truncated = step >= EnvTraits<VER>::MAX_STEPS;   // evaluated before the increment (:144-145)
         step += 1;
         ep_len = step;
@@ -325,8 +329,9 @@ template <typename Real, int VER>
 QS_HD void reset_env(EnvState<Real, VER>& s, const ResetConsts& rc, uint64_t seed, uint64_t env_gid) {
     constexpr int NWP = EnvState<Real, VER>::NWP;
     const double PI = 3.141592653589793;
-    double u[16];
-    reset_uniforms(seed, env_gid, s.episode, u);
+    constexpr int NU = VER == ENV_V2M ? 18 : 16;
+    double u[NU];
+    reset_uniforms<NU>(seed, env_gid, s.episode, u);
     int k = 0;
     double start[3];
     start[0] = uniform_rn(-1.0, 1.0, u[k++]);
@@ -345,37 +350,45 @@ QS_HD void reset_env(EnvState<Real, VER>& s, const ResetConsts& rc, uint64_t see
 #pragma unroll
     for (int j = 0; j < NWP; ++j) { s.wp[j][0] = Real(0); s.wp[j][1] = Real(0); s.wp[j][2] = Real(0); }
     int nwp = 1;
-    if (VER == ENV_V2) {
+    if (is_v2(VER)) {
+        if (VER == ENV_V2M) nwp = 2 + (int)floor(u[k++] * 2.0);    // num_waypoints = randint(2, 4), drawn where :46 has it
         k += 4;                           // roll, pitch, yaw draws and `rand() < 0`: consumed, unused (:49-52)
         int kind;
         if (u[k++] < 0.3) kind = 0;       // linear
         else if (u[k++] < 0.6) kind = 1;  // curved
         else kind = 2;                    // helical
-        nwp = 1;                          // self.num_waypoints = 1 (:47)
-        double w[3];
+        const int tb = nwp * (nwp - 1) / 2;                          // this K's row of the sin/cos tables
+        double end[3] = {0.0, 0.0, 0.0};
+        int axis = -1;
         if (kind <= 1) {
-            double end[3];
             end[0] = uniform_rn(-1.0, 1.0, u[k++]);
             end[1] = uniform_rn(-1.0, 1.0, u[k++]);
             k++;
             end[2] = uniform_rn(0.5, 3.0, u[k++]);
-            int axis = -1;
-            if (kind == 1) axis = 2 - (int)floor(u[k++] * 3.0);   // randint(0,3): 0 -> z, 1 -> y, 2 -> x
-            const double t = 1.0;                                   // i / num_waypoints, i = 1
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                w[i] = add_rn(start[i], mul_rn(t, end[i] - start[i]));
-                if (kind == 1 && i == axis) w[i] = add_rn(w[i], rc.sin_tab[0]);   // + sin(2*t*pi)
-            }
-            if (kind == 1) w[2] = fmax(w[2], 0.2);
-        } else {
-            w[0] = add_rn(start[0], mul_rn(0.8, rc.cos_tab[0]));
-            w[1] = add_rn(start[1], mul_rn(0.8, rc.sin_tab[0]));
-            w[2] = fmax(add_rn(start[2], 1 * 0.4), 0.2);
+            if (kind == 1) axis = 2 - (int)floor(u[k++] * 3.0);     // randint(0,3): 0 -> z, 1 -> y, 2 -> x
         }
-        s.wp[0][0] = (Real)w[0];
-        s.wp[0][1] = (Real)w[1];
-        s.wp[0][2] = (Real)w[2];
+#pragma unroll
+        for (int j = 0; j < NWP; ++j) {
+            if (j < nwp) {
+                double w[3];
+                if (kind <= 1) {
+                    const double t = (double)(j + 1) / (double)nwp;  // i / num_waypoints, i = 1..K (utils.py:19,37)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        w[i] = add_rn(start[i], mul_rn(t, end[i] - start[i]));
+                        if (kind == 1 && i == axis) w[i] = add_rn(w[i], rc.sin_tab[tb + j]);   // + sin(2*t*pi)
+                    }
+                    if (kind == 1) w[2] = fmax(w[2], 0.2);
+                } else {
+                    w[0] = add_rn(start[0], mul_rn(0.8, rc.cos_tab[tb + j]));
+                    w[1] = add_rn(start[1], mul_rn(0.8, rc.sin_tab[tb + j]));
+                    w[2] = fmax(add_rn(start[2], mul_rn((double)(j + 1), 0.4)), 0.2);
+                }
+                s.wp[j][0] = (Real)w[0];
+                s.wp[j][1] = (Real)w[1];
+                s.wp[j][2] = (Real)w[2];
+            }
+        }
         s.final_yaw = (Real)uniform_rn(-PI, PI, u[k++]);
     } else {
         nwp = 1 + (int)floor(u[k++] * 2.0);                         // randint(1,3)

@@ -67,9 +67,23 @@ inline StepParams<Real> base_params(const qs_handle* h) {
     for (int i = 0; i < 16; ++i) { m.mix[i] = (Real)c.mix[i]; m.inv_mix[i] = (Real)c.inv_mix[i]; }
     m.tmax = (Real)c.max_prop_thrust;
     m.tmin = (Real)c.min_prop_thrust;
-    for (int i = 0; i < 3; ++i) { p.rc.sin_tab[i] = c.sin_tab[i]; p.rc.cos_tab[i] = c.cos_tab[i]; }
+    for (int i = 0; i < QS_TRIG_TAB; ++i) { p.rc.sin_tab[i] = c.sin_tab[i]; p.rc.cos_tab[i] = c.cos_tab[i]; }
     return p;
 }
+
+// Which kernel variant a handle runs: ENV_V1, ENV_V2 (one waypoint, as shipped) or ENV_V2M (v2 with 2-3 waypoints).
+inline int env_variant(const qs_handle* h) {
+    return h->cfg.env_version == 2 ? (h->cfg.v2_random_waypoints ? ENV_V2M : ENV_V2) : ENV_V1;
+}
+// Run `body` with `constexpr int VER` bound to the handle's variant.
+#define QS_FOR_VARIANT(h, ...)                                                        \
+    do {                                                                              \
+        switch (qs::env_variant(h)) {                                                 \
+            case qs::ENV_V2: { constexpr int VER = qs::ENV_V2; __VA_ARGS__ } break;   \
+            case qs::ENV_V2M: { constexpr int VER = qs::ENV_V2M; __VA_ARGS__ } break; \
+            default: { constexpr int VER = qs::ENV_V1; __VA_ARGS__ } break;           \
+        }                                                                             \
+    } while (0)
 
 // Persistent grid: enough CTAs to fill every SM at the kernel's occupancy, never more than the work needs.
 template <typename Kernel>

@@ -218,14 +218,18 @@ QS_HD double u53(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-// The 16 unit uniforms a reset of (global env id, episode) may consume.
-QS_HD void reset_uniforms(uint64_t seed, uint64_t env_id, uint32_t episode, double* u16) {
+// The unit uniforms a reset of (global env id, episode) may consume: v2 with a drawn waypoint count needs 17, everything else
+// <= 16.  Kernels generate only the blocks their variant can consume (N = 16 or 18); the test hook returns all QS_N_UNIFORMS.
+#define QS_N_UNIFORMS 18
+template <int N = QS_N_UNIFORMS>
+QS_HD void reset_uniforms(uint64_t seed, uint64_t env_id, uint32_t episode, double* u /*[N]*/) {
+    static_assert(N % 2 == 0 && N <= QS_N_UNIFORMS, "two uniforms per Philox block");
 #pragma unroll
-    for (uint32_t j = 0; j < 8; ++j) {
+    for (uint32_t j = 0; j < N / 2; ++j) {
         uint32_t w[4];
         philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), episode, j, (uint32_t)seed, (uint32_t)(seed >> 32), w);
-        u16[2 * j] = u53(w[0], w[1]);
-        u16[2 * j + 1] = u53(w[2], w[3]);
+        u[2 * j] = u53(w[0], w[1]);
+        u[2 * j + 1] = u53(w[2], w[3]);
     }
 }
 

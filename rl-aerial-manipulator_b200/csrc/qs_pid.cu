@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) pid_kernel(const PidArgs a) {
     }
     if (a.des_vel) { dvel[0] = a.des_vel[e * 3]; dvel[1] = a.des_vel[e * 3 + 1]; dvel[2] = a.des_vel[e * 3 + 2]; }
     if (a.des_acc) { dacc[0] = a.des_acc[e * 3]; dacc[1] = a.des_acc[e * 3 + 1]; dacc[2] = a.des_acc[e * 3 + 2]; }
-    const double dyaw = a.des_yaw ? a.des_yaw[e] : (VER == ENV_V2 ? (double)st.final_yaw : 0.0);
+    const double dyaw = a.des_yaw ? a.des_yaw[e] : (is_v2(VER) ? (double)st.final_yaw : 0.0);
     const double dyawdot = a.des_yawdot ? a.des_yawdot[e] : 0.0;
     double I[6];
 #pragma unroll
@@ -135,11 +135,8 @@ int qs_pid_run(qs_handle* h, const qs_pid_gains* gains, double dt, const double*
     a.integral = integral; a.wrench = wrench_out; a.actions = actions_out; a.clip = clip_actions;
     const unsigned blocks = (unsigned)((a.n + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool f32 = h->cfg.precision == QS_F32, v2 = h->cfg.env_version == 2;
-    if (f32 && v2) pid_kernel<float, ENV_V2><<<blocks, 128, 0, st>>>(a);
-    else if (f32) pid_kernel<float, ENV_V1><<<blocks, 128, 0, st>>>(a);
-    else if (v2) pid_kernel<double, ENV_V2><<<blocks, 128, 0, st>>>(a);
-    else pid_kernel<double, ENV_V1><<<blocks, 128, 0, st>>>(a);
+    if (h->cfg.precision == QS_F32) QS_FOR_VARIANT(h, (pid_kernel<float, VER><<<blocks, 128, 0, st>>>(a)););
+    else QS_FOR_VARIANT(h, (pid_kernel<double, VER><<<blocks, 128, 0, st>>>(a)););
     err = cudaGetLastError();
     if (err != cudaSuccess) { set_error(h, "qs_pid_run: %s", cudaGetErrorString(err)); return QS_ECUDA; }
     return QS_OK;

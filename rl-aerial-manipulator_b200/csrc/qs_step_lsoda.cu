@@ -16,27 +16,16 @@ int launch_step_lsoda(qs_handle* h, const float* actions, float* obs, double* re
     p.ep_ret_out = ep_ret;
     p.ep_len_out = ep_len;
     unsigned grid = 0;
-    if (h->cfg.env_version == 2) {
+    QS_FOR_VARIANT(h,
         if (p.mom_partial) {
-            auto k = env_step_kernel<double, ENV_V2, INTEG_LSODA, true>;
+            auto k = env_step_kernel<double, VER, INTEG_LSODA, true>;
             grid = step_grid(h, k, STEP_BLOCK);
             k<<<grid, STEP_BLOCK, 0, st>>>(p);
         } else {
-            auto k = env_step_kernel<double, ENV_V2, INTEG_LSODA, false>;
+            auto k = env_step_kernel<double, VER, INTEG_LSODA, false>;
             grid = step_grid(h, k, STEP_BLOCK);
             k<<<grid, STEP_BLOCK, 0, st>>>(p);
-        }
-    } else {
-        if (p.mom_partial) {
-            auto k = env_step_kernel<double, ENV_V1, INTEG_LSODA, true>;
-            grid = step_grid(h, k, STEP_BLOCK);
-            k<<<grid, STEP_BLOCK, 0, st>>>(p);
-        } else {
-            auto k = env_step_kernel<double, ENV_V1, INTEG_LSODA, false>;
-            grid = step_grid(h, k, STEP_BLOCK);
-            k<<<grid, STEP_BLOCK, 0, st>>>(p);
-        }
-    }
+        });
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error(h, "env_step_kernel<lsoda> launch failed: %s", cudaGetErrorString(err));

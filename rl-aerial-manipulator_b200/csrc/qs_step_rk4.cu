@@ -1,5 +1,5 @@
 // qs_step_rk4.cu -- instantiations of the fused env-step kernel with the fixed-step RK4 integrator
-// (throughput mode), float32 and float64, env v1 and v2.
+// (throughput mode), float32 and float64, env v1, v2 and v2 with 2-3 waypoints.
 #include "qs_internal.cuh"
 #include <stdlib.h>
 
@@ -19,27 +19,16 @@ static int launch_rk4(qs_handle* h, const float* actions, float* obs, Real* rewa
     p.ls_counters = nullptr;
     p.ls_steps = nullptr;
     unsigned grid = 0;
-    if (h->cfg.env_version == 2) {
+    QS_FOR_VARIANT(h,
         if (p.mom_partial) {
-            auto k = env_step_kernel<Real, ENV_V2, INTEG_RK4, true>;
+            auto k = env_step_kernel<Real, VER, INTEG_RK4, true>;
             grid = step_grid(h, k, STEP_BLOCK);
             k<<<grid, STEP_BLOCK, 0, st>>>(p);
         } else {
-            auto k = env_step_kernel<Real, ENV_V2, INTEG_RK4, false>;
+            auto k = env_step_kernel<Real, VER, INTEG_RK4, false>;
             grid = step_grid(h, k, STEP_BLOCK);
             k<<<grid, STEP_BLOCK, 0, st>>>(p);
-        }
-    } else {
-        if (p.mom_partial) {
-            auto k = env_step_kernel<Real, ENV_V1, INTEG_RK4, true>;
-            grid = step_grid(h, k, STEP_BLOCK);
-            k<<<grid, STEP_BLOCK, 0, st>>>(p);
-        } else {
-            auto k = env_step_kernel<Real, ENV_V1, INTEG_RK4, false>;
-            grid = step_grid(h, k, STEP_BLOCK);
-            k<<<grid, STEP_BLOCK, 0, st>>>(p);
-        }
-    }
+        });
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error(h, "env_step_kernel launch failed: %s", cudaGetErrorString(err));
@@ -79,7 +68,8 @@ int launch_step_f32(qs_handle* h, const float* actions, float* obs, float* rewar
     p.ep_len_out = ep_len;
     p.ls_counters = nullptr;
     p.ls_steps = nullptr;
-    const unsigned grid = h->cfg.env_version == 2 ? launch_tma<ENV_V2>(h, p, st) : launch_tma<ENV_V1>(h, p, st);
+    unsigned grid = 0;
+    QS_FOR_VARIANT(h, grid = launch_tma<VER>(h, p, st););
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error(h, "env_step_tma_kernel launch failed: %s", cudaGetErrorString(err));

@@ -64,9 +64,10 @@ class WaypointQuadEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, env_version: int = 2, obs_scaled: bool = True, precision: str = "f64", integrator: str = "lsoda",
-                 substeps: int = 1, device: int | None = None, seed: int = 0):
+                 substeps: int = 1, device: int | None = None, seed: int = 0, v2_random_waypoints: bool = False):
         self._sim = BatchedQuadEnv(1, env_version=env_version, precision=precision, integrator=integrator, substeps=substeps,
-                                   obs_scaled=obs_scaled, auto_reset=False, device=device, seed=seed)
+                                   obs_scaled=obs_scaled, auto_reset=False, device=device, seed=seed,
+                                   v2_random_waypoints=v2_random_waypoints)
         d = self._sim.obs_dim
         self.observation_space = _box(-np.inf, np.inf, (d,), np.float32)
         self.action_space = _box(np.array([0, -1, -1, -1], dtype=np.float32), np.array([2.0, 1, 1, 1], dtype=np.float32))

@@ -65,7 +65,7 @@ class HostHarness:
                          int(st.get("final_reached", False)), int(has_last), st.get("episode", 0)], dtype=np.int32)
         reals = np.array([ld if has_last else 0.0, st.get("final_yaw", 0.0), st.get("ep_return", 0.0)], dtype=np.float64)
         act = np.ascontiguousarray(act, dtype=np.float32)
-        obs = np.zeros(20 if version == 2 else 17, dtype=np.float32)
+        obs = np.zeros(20 if version in (2, 3) else 17, dtype=np.float32)
         rew = C.c_double()
         flags = C.c_int()
         ep_len = C.c_int()
@@ -83,13 +83,13 @@ class HostHarness:
         wp = np.zeros(9)
         ints = np.zeros(7, dtype=np.int32)
         reals = np.zeros(3)
-        obs = np.zeros(20 if version == 2 else 17, dtype=np.float32)
+        obs = np.zeros(20 if version in (2, 3) else 17, dtype=np.float32)
         self.lib.hh_reset(version, int(obs_scaled), env_gid, episode, ptr(y), ptr(wp), ptr(ints), ptr(reals), ptr(obs))
         return dict(y=y, wp_list=wp.reshape(3, 3), n_wp=int(ints[0]), wp_index=int(ints[1]), current_step=int(ints[2]),
                     counter=int(ints[3]), final_reached=bool(ints[4]), has_last=bool(ints[5]), final_yaw=reals[1]), obs
 
     def uniforms(self, seed, env_gid, episode):
-        u = np.zeros(16)
+        u = np.zeros(18)
         self.lib.hh_uniforms(seed, env_gid, episode, ptr(u))
         return u
 

@@ -79,7 +79,7 @@ extern "C" {
 void hh_configure(const qs_config* c) {
     fill(g_model_d, c);
     fill(g_model_f, c);
-    for (int i = 0; i < 3; ++i) { g_rc.sin_tab[i] = c->sin_tab[i]; g_rc.cos_tab[i] = c->cos_tab[i]; }
+    for (int i = 0; i < QS_TRIG_TAB; ++i) { g_rc.sin_tab[i] = c->sin_tab[i]; g_rc.cos_tab[i] = c->cos_tab[i]; }
     lsoda_tables_init(g_tables);
     g_rtol = c->lsoda_rtol; g_atol = c->lsoda_atol; g_seed = c->seed;
 }
@@ -100,7 +100,11 @@ void hh_mix(const float* act, int scale_f32, double* F, double* M) {
 
 void hh_step(int version, int f32, int integ, int substeps, int scale_f32, int obs_scaled, double* y, double* wp, int* ints, double* reals,
              const float* act, float* obs, double* reward, int* flags, int* ep_len, int* ls_int, double* ls_dbl) {
-    if (version == 2) {
+    // version 3 = v2 with 2-3 waypoints (ENV_V2M)
+    if (version == 3) {
+        if (f32) host_step<float, ENV_V2M>(g_model_f, integ, substeps, scale_f32, obs_scaled, y, wp, ints, reals, act, obs, reward, flags, ep_len, ls_int, ls_dbl);
+        else host_step<double, ENV_V2M>(g_model_d, integ, substeps, scale_f32, obs_scaled, y, wp, ints, reals, act, obs, reward, flags, ep_len, ls_int, ls_dbl);
+    } else if (version == 2) {
         if (f32) host_step<float, ENV_V2>(g_model_f, integ, substeps, scale_f32, obs_scaled, y, wp, ints, reals, act, obs, reward, flags, ep_len, ls_int, ls_dbl);
         else host_step<double, ENV_V2>(g_model_d, integ, substeps, scale_f32, obs_scaled, y, wp, ints, reals, act, obs, reward, flags, ep_len, ls_int, ls_dbl);
     } else {
@@ -110,7 +114,12 @@ void hh_step(int version, int f32, int integ, int substeps, int scale_f32, int o
 }
 
 void hh_reset(int version, int obs_scaled, uint64_t env_gid, int episode, double* y, double* wp, int* ints, double* reals, float* obs) {
-    if (version == 2) {
+    if (version == 3) {
+        EnvState<double, ENV_V2M> s; s.episode = (uint32_t)episode;
+        reset_env<double, ENV_V2M>(s, g_rc, g_seed, env_gid);
+        make_obs<double, ENV_V2M>(s, obs_scaled, obs);
+        unload<double, ENV_V2M>(s, y, wp, ints, reals);
+    } else if (version == 2) {
         EnvState<double, ENV_V2> s; s.episode = (uint32_t)episode;
         reset_env<double, ENV_V2>(s, g_rc, g_seed, env_gid);
         make_obs<double, ENV_V2>(s, obs_scaled, obs);
@@ -123,7 +132,7 @@ void hh_reset(int version, int obs_scaled, uint64_t env_gid, int episode, double
     }
 }
 
-void hh_uniforms(uint64_t seed, uint64_t env_gid, uint32_t episode, double* u16) { reset_uniforms(seed, env_gid, episode, u16); }
+void hh_uniforms(uint64_t seed, uint64_t env_gid, uint32_t episode, double* u /*[QS_N_UNIFORMS]*/) { reset_uniforms(seed, env_gid, episode, u); }
 
 void hh_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out); }
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 18, names
     for n in names:
         assert hasattr(lib, n), f"libquadsim.so does not export {n}"
-    assert lib.qs_abi_version() == 1
+    assert lib.qs_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure path")
@@ -52,6 +52,7 @@ def test_config_constants_match_reference_values():
     np.testing.assert_allclose(np.array(c.inv_inertia[:]).reshape(3, 3) @ np.array(c.inertia[:]).reshape(3, 3), np.eye(3), atol=1e-12)
     np.testing.assert_allclose(np.array(c.inv_mix[:]).reshape(4, 4) @ np.array(c.mix[:]).reshape(4, 4), np.eye(4), atol=1e-12)
     assert c.sin_tab[0] == np.sin(2 * np.pi) and c.cos_tab[0] == 1.0 and c.lsoda_rtol == 1.49012e-8
+    assert c.sin_tab[1] == np.sin(2 * 0.5 * np.pi) and c.sin_tab[3] == np.sin(2 * (1 / 3) * np.pi) and c.cos_tab[4] == np.cos((2 / 3) * (2 * np.pi * 1))
     # values quoted in SURVEY.md section 8(a)
     assert abs(c.inv_inertia[0] - 4000.278) < 1e-3 and abs(c.inv_inertia[8] - 2675.414) < 1e-3 and abs(c.mix[12] - 0.0245499) < 1e-7
 

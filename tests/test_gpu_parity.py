@@ -16,12 +16,15 @@ from oracle import quad_oracle as qo
 
 pytestmark = pytest.mark.gpu
 
-VERS = {"v2": 2, "v1": 1, "v1_raw": 1}
+VERS = {"v2": 2, "v1": 1, "v1_raw": 1, "v2m": 2}   # v2m: v2 with 2-3 waypoints (rl_env_scaledObs.py:46 alternative), ENV_V2M kernels
+GOLDEN_OF = {"v2m": "v2"}
 
 
 def make_env(n, variant="v2", **kw):
     from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
     kw.setdefault("obs_scaled", variant != "v1_raw")
+    if variant == "v2m":
+        kw["v2_random_waypoints"] = True
     return BatchedQuadEnv(n, env_version=VERS[variant], **kw)
 
 
@@ -32,7 +35,7 @@ def load(golden_dir, name):
 def golden_select(g, variant):
     """Indices of golden cases the kernel layout can hold (v2 keeps one waypoint, like the shipped reference)."""
     idx = np.arange(len(g["reward"]))
-    if VERS[variant] == 2:
+    if variant == "v2":
         idx = idx[g["pre_n_wp"] == 1]
     return idx
 
@@ -58,10 +61,11 @@ def t2n(t):
 # ------------------------------------------------------------------------------------------------------
 # (a) golden vectors of the unmodified reference
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", ["v2", "v1", "v1_raw"])
+@pytest.mark.parametrize("variant", ["v2", "v1", "v1_raw", "v2m"])
 def test_f64_lsoda_single_step_vs_reference(golden_dir, variant):
-    """float64 + LSODA port: state, obs and reward within 1e-9 of the reference's step; flags bit-exact."""
-    g = load(golden_dir, f"step_{variant}.npz")
+    """float64 + LSODA port: state, obs and reward within 1e-9 of the reference's step; flags bit-exact.
+    v2m runs ALL v2 cases, including the reference's multi-waypoint lists (2 and 3 entries), on the ENV_V2M kernels."""
+    g = load(golden_dir, f"step_{GOLDEN_OF.get(variant, variant)}.npz")
     idx = golden_select(g, variant)
     env = make_env(len(idx), variant, precision="f64", integrator="lsoda", auto_reset=False)
     inject_golden(env, g, idx)
@@ -74,7 +78,7 @@ def test_f64_lsoda_single_step_vs_reference(golden_dir, variant):
     np.testing.assert_allclose(st["y"], g["post_y"][idx], rtol=1e-9, atol=1e-10)
     np.testing.assert_array_equal(st["wp_index"], g["post_wp_index"][idx])
     np.testing.assert_array_equal(st["current_step"], g["post_current_step"][idx])
-    if variant == "v2":
+    if variant in ("v2", "v2m"):
         np.testing.assert_array_equal(st["counter"], g["post_counter"][idx])
         np.testing.assert_array_equal(st["final_reached"], g["post_final_reached"][idx].astype(np.uint8))
     np.testing.assert_allclose(st["last_distance"], g["post_last_distance"][idx], rtol=1e-9, atol=1e-10)
@@ -88,10 +92,10 @@ def test_f64_lsoda_single_step_vs_reference(golden_dir, variant):
     env.close()
 
 
-@pytest.mark.parametrize("variant", ["v2", "v1"])
+@pytest.mark.parametrize("variant", ["v2", "v1", "v2m"])
 def test_f32_rk4_single_step_vs_reference(golden_dir, variant):
     """float32 throughput mode vs the float64 reference: 1e-4 relative; flags equal."""
-    g = load(golden_dir, f"step_{variant}.npz")
+    g = load(golden_dir, f"step_{GOLDEN_OF.get(variant, variant)}.npz")
     idx = golden_select(g, variant)
     idx = idx[g["case"][idx] != "on_waypoint_nan"]
     env = make_env(len(idx), variant, precision="f32", integrator="rk4", substeps=1, auto_reset=False)
@@ -239,7 +243,7 @@ def test_f32_rk4_vs_oracle_65536(variant):
     env.close()
 
 
-@pytest.mark.parametrize("variant", ["v2", "v1"])
+@pytest.mark.parametrize("variant", ["v2", "v1", "v2m"])
 def test_reset_matches_oracle_on_device_uniforms(variant):
     """Reset sampling: the kernel's Philox uniforms, replayed through the (reference-pinned) oracle reset."""
     n = 4099  # ragged: not a multiple of the warp or block size
@@ -248,15 +252,18 @@ def test_reset_matches_oracle_on_device_uniforms(variant):
     ids = torch.arange(n, dtype=torch.int64) + 5_000_000_000
     U = t2n(env.reset_uniforms(ids, torch.zeros(n, dtype=torch.int32)))
     assert U.min() >= 0 and U.max() < 1 and abs(U.mean() - 0.5) < 0.01
-    b = qo.EnvBatch.empty(variant, n, max_wp=3)
+    b = qo.EnvBatch.empty(GOLDEN_OF.get(variant, variant), n, max_wp=3)
+    b.v2_random_waypoints = variant == "v2m"
     qo.reset_from_uniforms(b, np.arange(n), U)
     st = {k: t2n(v) for k, v in env.get_state().items()}
     np.testing.assert_array_equal(st["y"], b.y)
-    k = 1 if variant == "v2" else 2
+    k = {"v2": 1, "v1": 2, "v2m": 3}[variant]
     np.testing.assert_array_equal(st["wp_list"][:, :k], b.wp_list[:, :k])
     np.testing.assert_array_equal(st["n_wp"], b.n_wp)
+    if variant == "v2m":
+        assert set(np.unique(st["n_wp"])) == {2, 3}
     assert np.all(np.isnan(st["last_distance"])) and np.all(st["current_step"] == 0) and np.all(st["episode"] == 0)
-    if variant == "v2":
+    if variant in ("v2", "v2m"):
         np.testing.assert_array_equal(st["final_yaw"], b.final_yaw)
     np.testing.assert_array_equal(obs, qo.observe(b))
     # masked reset touches only the masked envs and advances their episode counter
@@ -271,7 +278,7 @@ def test_reset_matches_oracle_on_device_uniforms(variant):
     env.close()
 
 
-@pytest.mark.parametrize("variant", ["v2", "v1"])
+@pytest.mark.parametrize("variant", ["v2", "v1", "v2m"])
 def test_vec_rollout_with_autoreset_vs_oracle(variant):
     """N envs, random actions, auto-reset inside the kernel: the oracle (scipy LSODA) driven by the very same
     Philox uniforms must see the same dones, terminal observations, episode returns/lengths and next obs."""
@@ -282,7 +289,7 @@ def test_vec_rollout_with_autoreset_vs_oracle(variant):
     def uniforms(ids, eps):
         return t2n(env.reset_uniforms(torch.as_tensor(ids, dtype=torch.int64), torch.as_tensor(eps, dtype=torch.int32)))
 
-    vec = qo.VecOracle(variant, n, uniforms, integrator="lsoda", max_wp=3)
+    vec = qo.VecOracle(GOLDEN_OF.get(variant, variant), n, uniforms, integrator="lsoda", max_wp=3, v2_random_waypoints=(variant == "v2m"))
     obs_o = vec.reset()
     obs_k = t2n(env.reset()).copy()
     np.testing.assert_array_equal(obs_k, obs_o)
@@ -337,6 +344,35 @@ def test_properties_1M_envs_f32():
     assert int(ep_done[: n // 2].sum()) > n // 4
     assert (st["current_step"] <= n_steps).all() and (st["y"][:, 2] > -1).all()
     env.close()
+
+
+def test_config5_total_size_on_one_gpu_matches_small_batches():
+    """8,388,608 envs (BASELINE configs[4] total) in one handle: 64-bit addressing of the pool and obs, and the same episodes as
+    small handles placed at the head, in the middle and at the tail of the global env-id range (Philox keyed on the global id)."""
+    n = 8 * (1 << 20)
+    big = make_env(n, "v2", precision="f32", seed=4)
+    big.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    acts = [(torch.rand((n, 4), device="cuda", generator=g) * torch.tensor([0.7, 2, 2, 2], device="cuda")
+             - torch.tensor([0, 1, 1, 1.0], device="cuda")) for _ in range(2)]
+    small = {}
+    m = 4096
+    for off in (0, n // 2 + 31, n - m):
+        from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+        small[off] = BatchedQuadEnv(m, env_version=2, precision="f32", seed=4, env_id_offset=off)
+        small[off].reset()
+    for t in range(120):
+        a = acts[t & 1]
+        out = big.step(a)
+        for off, env in small.items():
+            o = env.step(a[off:off + m].contiguous())
+            assert torch.equal(o.obs, out.obs[off:off + m]) and torch.equal(o.flags, out.flags[off:off + m]), (t, off)
+            assert torch.equal(o.reward, out.reward[off:off + m])
+    assert torch.isfinite(out.obs).all()
+    assert int((big.get_state(["episode"])["episode"] > 0).sum()) > n // 10      # low thrust: many crash and reset
+    big.close()
+    for env in small.values():
+        env.close()
 
 
 def test_determinism_and_shard_independence():

@@ -78,9 +78,8 @@ def test_f64_lsoda_step_vs_reference_golden(hh, golden_dir, variant):
     ver = VERS[variant]
     checked = 0
     for i in range(len(g["reward"])):
-        if ver == 2 and g["pre_n_wp"][i] > 1:
-            continue  # multi-waypoint v2 lists are the reference's commented-out alternative; kernel holds 1
-        st, obs, rew, flags, ep_len, ls = hh.step(ver, golden_state(g, "pre_", i), g["action"][i], f32=False, integ="lsoda",
+        v = 3 if ver == 2 and g["pre_n_wp"][i] > 1 else ver   # multi-waypoint v2 lists: the ENV_V2M variant (wider record)
+        st, obs, rew, flags, ep_len, ls = hh.step(v, golden_state(g, "pre_", i), g["action"][i], f32=False, integ="lsoda",
                                                  obs_scaled=(variant != "v1_raw"))
         case = g["case"][i]
         np.testing.assert_allclose(st["y"], g["post_y"][i], rtol=1e-9, atol=1e-10, err_msg=f"{i} {case}")
@@ -108,9 +107,8 @@ def test_step_logic_exact_on_reference_state(hh, golden_dir, variant):
     with np.errstate(all="ignore"):
         obs_o, rew_o, term_o, trunc_o, info_o = qo.step(b, g["action"], integrator="rk4", substeps=4)
     for i in range(len(g["reward"])):
-        if ver == 2 and g["pre_n_wp"][i] > 1:
-            continue
-        st, obs, rew, flags, ep_len, _ = hh.step(ver, golden_state(g, "pre_", i), g["action"][i], f32=False, integ="rk4", substeps=4)
+        v = 3 if ver == 2 and g["pre_n_wp"][i] > 1 else ver
+        st, obs, rew, flags, ep_len, _ = hh.step(v, golden_state(g, "pre_", i), g["action"][i], f32=False, integ="rk4", substeps=4)
         np.testing.assert_allclose(st["y"], b.y[i], rtol=1e-12, atol=1e-13)
         if g["case"][i] == "on_waypoint_nan":
             continue
@@ -165,6 +163,36 @@ def test_reset_matches_oracle_on_same_uniforms(hh, variant):
         np.testing.assert_array_equal(obs, obs_o[e])
         kinds.add(int(b.n_wp[e]) if ver == 1 else (0 if U[e, 8] < 0.3 else 1 if U[e, 9] < 0.6 else 2))
     assert len(kinds) == (3 if ver == 2 else 2)
+
+
+def test_reset_v2_multi_waypoint_matches_oracle_and_reference(hh, golden_dir):
+    """ENV_V2M reset (num_waypoints = randint(2, 4), rl_env_scaledObs.py:46): the oracle reproduces the reference's reset with that
+    line enabled bit for bit on the golden uniform blocks, and the device code reproduces the oracle on its own Philox uniforms."""
+    g = load(golden_dir, "reset_v2m.npz")
+    n = g["uniforms"].shape[0]
+    b = qo.EnvBatch.empty("v2", n, max_wp=3)
+    b.v2_random_waypoints = True
+    qo.reset_from_uniforms(b, np.arange(n), g["uniforms"])
+    for f in ("y", "wp_list", "n_wp", "final_yaw"):
+        np.testing.assert_array_equal(getattr(b, f), g[f], err_msg=f)
+    np.testing.assert_array_equal(qo.observe(b), g["obs"])
+    assert set(np.unique(g["n_wp"])) == {2, 3}
+    m = 400
+    b = qo.EnvBatch.empty("v2", m, max_wp=3)
+    b.v2_random_waypoints = True
+    U = np.array([hh.uniforms(1234, 5_000_000_000 + e, e % 3) for e in range(m)])   # 1234: the seed the harness is configured with
+    qo.reset_from_uniforms(b, np.arange(m), U)
+    obs_o = qo.observe(b)
+    seen = set()
+    for e in range(m):
+        st, obs = hh.reset(3, 5_000_000_000 + e, e % 3)
+        assert st["n_wp"] == b.n_wp[e] and st["n_wp"] in (2, 3)
+        np.testing.assert_array_equal(st["y"], b.y[e])
+        np.testing.assert_array_equal(st["wp_list"][:st["n_wp"]], b.wp_list[e][:st["n_wp"]])
+        assert st["final_yaw"] == b.final_yaw[e]
+        np.testing.assert_array_equal(obs, obs_o[e])
+        seen.add((st["n_wp"], 0 if U[e, 9] < 0.3 else 1 if U[e, 10] < 0.6 else 2))
+    assert len(seen) == 6
 
 
 def test_reset_known_answers_from_reference(hh, golden_dir):

@@ -38,12 +38,12 @@ def _bind(lib):
     lib._gae_bound = True
 
 
-def gae(rewards, values, episode_starts, last_values, last_dones, gamma: float, gae_lambda: float):
-    """advantages, returns = GAE over time-major device buffers [T, N] (qs_gae)."""
+def gae(rewards, values, episode_starts, last_values, last_dones, gamma: float, gae_lambda: float, out=None):
+    """advantages, returns = GAE over time-major device buffers [T, N] (qs_gae); out = (advantages, returns) to reuse buffers."""
     lib = load_library()
     _bind(lib)
     T, n = rewards.shape
-    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    adv, ret = out if out is not None else (torch.empty_like(rewards), torch.empty_like(rewards))
     p = lambda t: C.c_void_p(t.data_ptr())
     for t in (rewards, values, episode_starts, last_values, last_dones):
         assert t.is_contiguous() and t.is_cuda
@@ -124,7 +124,10 @@ class QuadPPO:
     def __init__(self, env, vecnorm=None, state_dict: dict | None = None, n_steps: int = 64, batch_size: int = 65536, n_epochs: int = 10,
                  gamma: float = 0.995, gae_lambda: float = 0.9, clip_range: float = 0.2, ent_coef: float = 0.01, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 2e-4, normalize_advantage: bool = True, seed: int = 0,
-                 policy_impl: str = "auto"):
+                 policy_impl: str = "auto", graph_update: bool = True):
+        """graph_update: replay every minibatch update (gather, forward, loss, backward, gradient clipping, Adam) from one CUDA graph
+        -- at SB3-size minibatches (128) the ~60 launches of an eager update are pure launch latency.  Single rank only; with
+        several ranks the update runs eagerly around the NCCL gradient all-reduce."""
         self.env, self.vecnorm = env, vecnorm
         self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
         self.gamma, self.gae_lambda, self.clip_range = gamma, gae_lambda, clip_range
@@ -132,7 +135,10 @@ class QuadPPO:
         dev, n, d = env.device, env.n_envs, env.obs_dim
         sd = state_dict or init_state_dict(d, seed)
         self.net = TorchActorCritic(sd, d).to(dev)
-        self.opt = torch.optim.Adam(self.net.parameters(), lr=learning_rate, eps=1e-5)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.graph_update = bool(graph_update) and self.world == 1
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=learning_rate, eps=1e-5, capturable=self.graph_update)
+        self._graph = None
         self.policy = MlpPolicyKernel(sd, d, dev, impl=policy_impl)
         self.gen = torch.Generator(device=dev).manual_seed(seed + 1000 * (dist.get_rank() if dist.is_initialized() else 0))
         T = n_steps
@@ -148,7 +154,6 @@ class QuadPPO:
         self._ep_stats = torch.zeros(2, dtype=torch.float64, device=dev)
         self._zero = torch.zeros((), dtype=torch.float64, device=dev)
         self.ep_rew_mean, self.ep_count = float("nan"), 0
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
 
     # ---- rollout -------------------------------------------------------------------------------------
     def _forward(self, obs_raw, noise, obs_norm_out=None):
@@ -192,43 +197,88 @@ class QuadPPO:
             self._ep_stats[1] += done.sum()                                                     # reduced on device: no per-step sync
             self._last_obs = out.obs
         last_values = self._forward(self._last_obs, None)[1].clone()
-        self.advantages, self.returns = gae(self.rewards, self.values, self.episode_starts, last_values, self._last_dones,
-                                            self.gamma, self.gae_lambda)
+        if getattr(self, "advantages", None) is None:            # persistent: the captured update graph reads these addresses
+            self.advantages, self.returns = torch.empty_like(self.rewards), torch.empty_like(self.rewards)
+        gae(self.rewards, self.values, self.episode_starts, last_values, self._last_dones, self.gamma, self.gae_lambda,
+            out=(self.advantages, self.returns))
         self.num_timesteps += self.n_steps * env.n_envs * self.world
         s, c = self._ep_stats.tolist()
         self.ep_rew_mean = s / c if c > 0 else float("nan")     # mean return of the episodes that finished in this rollout
         self.ep_count = int(c)
 
     # ---- update --------------------------------------------------------------------------------------
+    def _minibatch_update(self, obs, act, oldlp, adv, ret):
+        values, logp, entropy = self.net.evaluate_actions(obs, act)
+        loss, pg, vf, ent = ppo_loss(values, logp, entropy, oldlp, adv, ret, self.clip_range, self.ent_coef, self.vf_coef,
+                                     self.normalize_advantage)
+        self.opt.zero_grad(set_to_none=False)
+        loss.backward()
+        if self.world > 1:                                   # data-parallel: average the 30,537 gradients over NVLink
+            flat_g = torch.cat([p.grad.reshape(-1) for p in self.net.parameters()])
+            dist.all_reduce(flat_g)
+            flat_g /= self.world
+            o = 0
+            for p in self.net.parameters():
+                p.grad.copy_(flat_g[o:o + p.numel()].view_as(p))
+                o += p.numel()
+        nn.utils.clip_grad_norm_(self.net.parameters(), self.max_grad_norm)
+        self.opt.step()
+        return loss.detach(), pg.detach(), vf.detach(), ent.detach()
+
+    def _build_update_graph(self, flat, bs):
+        """Capture one minibatch update over static buffers: idx -> gathers -> forward/backward -> clip -> Adam."""
+        import copy
+        obs, act, oldlp, adv, ret = flat
+        dev = obs.device
+        self._idx = torch.zeros(bs, dtype=torch.int64, device=dev)
+        net_sd = copy.deepcopy(self.net.state_dict())
+        opt_saved = {q: {k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for q, st in self.opt.state.items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                          # warm-up off the capture stream (allocations, autotuning, Adam state)
+            for _ in range(3):
+                self._minibatch_update(obs[self._idx], act[self._idx], oldlp[self._idx], adv[self._idx], ret[self._idx])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.net.load_state_dict(net_sd)                       # the warm-up steps must not count as training: parameters and Adam
+        for q, st in self.opt.state.items():                   # state go back IN PLACE (the graph captures their addresses; state
+            for k, v in st.items():                            # created lazily inside the capture would be re-zeroed by every replay)
+                if torch.is_tensor(v):
+                    if q in opt_saved:
+                        v.copy_(opt_saved[q][k])
+                    else:
+                        v.zero_()
+        self._graph_src = flat
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._graph_stats = self._minibatch_update(obs[self._idx], act[self._idx], oldlp[self._idx], adv[self._idx], ret[self._idx])
+        self._graph = g
+
     def train(self) -> dict:
         T, n = self.rewards.shape
         total = T * n
         flat = lambda x: x.reshape(total, *x.shape[2:])
         obs, act, oldv, oldlp, adv, ret = map(flat, (self.obs, self.actions, self.values, self.logp, self.advantages, self.returns))
         bs = min(self.batch_size, total)
-        stats = {}
+        stats = None
+        if self.graph_update and self._graph is None:
+            # the rollout buffers (and GAE outputs) keep their addresses between iterations, so one capture serves the whole run
+            self._build_update_graph((obs, act, oldlp, adv, ret), bs)
+        if self.graph_update and any(a.data_ptr() != b.data_ptr() for a, b in zip(self._graph_src, (obs, act, oldlp, adv, ret))):
+            self._build_update_graph((obs, act, oldlp, adv, ret), bs)
         for epoch in range(self.n_epochs):
             perm = torch.randperm(total, device=obs.device, generator=self.gen)
             for start in range(0, total - bs + 1, bs):
-                idx = perm[start:start + bs]
-                values, logp, entropy = self.net.evaluate_actions(obs[idx], act[idx])
-                loss, pg, vf, ent = ppo_loss(values, logp, entropy, oldlp[idx], adv[idx], ret[idx], self.clip_range, self.ent_coef,
-                                             self.vf_coef, self.normalize_advantage)
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                if self.world > 1:                                   # data-parallel: average the 30,537 gradients over NVLink
-                    flat_g = torch.cat([p.grad.reshape(-1) for p in self.net.parameters()])
-                    dist.all_reduce(flat_g)
-                    flat_g /= self.world
-                    o = 0
-                    for p in self.net.parameters():
-                        p.grad.copy_(flat_g[o:o + p.numel()].view_as(p))
-                        o += p.numel()
-                nn.utils.clip_grad_norm_(self.net.parameters(), self.max_grad_norm)
-                self.opt.step()
-                stats = {"loss": loss.detach(), "policy_gradient_loss": pg.detach(), "value_loss": vf.detach(), "entropy_loss": ent.detach()}
+                if self.graph_update:
+                    self._idx.copy_(perm[start:start + bs])
+                    self._graph.replay()
+                    stats = self._graph_stats
+                else:
+                    idx = perm[start:start + bs]
+                    stats = self._minibatch_update(obs[idx], act[idx], oldlp[idx], adv[idx], ret[idx])
         self.policy.params.copy_(self.net.packed())                  # the rollout kernels read the updated weights
-        return {k: float(v) for k, v in stats.items()}
+        keys = ("loss", "policy_gradient_loss", "value_loss", "entropy_loss")
+        return {k: float(v) for k, v in zip(keys, stats)}
 
     def learn(self, total_timesteps: int, log=None):
         while self.num_timesteps < total_timesteps:

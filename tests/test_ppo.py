@@ -98,3 +98,21 @@ def test_quad_ppo_iterations_run_and_kernel_tracks_torch_weights():
     a_k, v_k, _ = ppo.policy.forward(obs.contiguous())
     assert float((v_k - v_t).abs().max()) < 5e-3
     env.close()
+
+
+@pytest.mark.gpu
+def test_graph_replayed_update_equals_eager_update():
+    """The CUDA-graph replay of the minibatch update (gather, forward, loss, backward, clipping, Adam) must reproduce the eager
+    update: same seeds, same rollouts -> same parameters after two iterations (same kernels in the same order)."""
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    from rl_aerial_manipulator_b200.ppo import QuadPPO
+    params = {}
+    for graph in (False, True):
+        env = BatchedQuadEnv(64, env_version=1, precision="f32", seed=3)
+        ppo = QuadPPO(env, n_steps=64, batch_size=128, n_epochs=3, policy_impl="fp32", seed=5, graph_update=graph)
+        logs = []
+        ppo.learn(2 * 64 * 64, log=logs.append)
+        assert len(logs) == 2 and all(math.isfinite(v) for l in logs for k, v in l.items() if k.endswith("loss"))
+        params[graph] = ppo.net.packed().clone()
+        env.close()
+    assert float((params[True] - params[False]).abs().max()) < 1e-5

@@ -140,6 +140,15 @@ int qs_step(qs_handle* h, const float* actions, float* obs_out, void* reward_out
             float* terminal_obs_out, void* ep_return_out, int32_t* ep_len_out, void* stream);
 
 /*
+ * qs_step on the env sub-range [first_env, first_env + count) only; every buffer pointer refers to the sub-range's first env.
+ * first_env must be a multiple of 32 (the pool is tiled per warp).  Sub-ranges are independent, so a host-facing caller can
+ * pipeline chunks on several streams: actions of chunk c+1 go up while chunk c steps and its observations come down
+ * (vec_env.QuadVecEnv(pipeline_chunks=...)).  RK4 only; not available while qs_step_moments is armed.
+ */
+int qs_step_range(qs_handle* h, int64_t first_env, int64_t count, const float* actions, float* obs_out, void* reward_out,
+                  uint8_t* flags_out, float* terminal_obs_out, void* ep_return_out, int32_t* ep_len_out, void* stream);
+
+/*
  * Fused VecNormalize moments: after this call every qs_step also leaves (n, mean[D], M2[D]) of the observations it
  * returned (f64[1+2D], device, caller-owned) in `moments_out` -- what RunningMeanStd.update(obs) needs -- computed inside the
  * step kernel from the obs tile it already holds.  shift_stats: VecNormalize stats f64[1+2D] whose mean is used as the

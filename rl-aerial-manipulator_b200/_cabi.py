@@ -113,6 +113,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.qs_state_bytes_per_env.restype = i64
     lib.qs_reset.argtypes = [vp, vp, vp, vp]
     lib.qs_step.argtypes = [vp] + [vp] * 7 + [vp]
+    lib.qs_step_range.argtypes = [vp, i64, i64] + [vp] * 7 + [vp]
+    lib.qs_step_range.restype = C.c_int
     lib.qs_step_moments.argtypes = [vp, vp, vp]
     lib.qs_step_moments_merge.argtypes = [vp, vp]
     lib.qs_step_moments_merge.restype = C.c_int

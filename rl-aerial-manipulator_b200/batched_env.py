@@ -131,6 +131,19 @@ class BatchedQuadEnv:
                                p(self.ep_return), p(self.ep_len), self._stream()), "qs_step")
         return StepOut(self.obs, self.reward, self.flags, self.terminal_obs, self.ep_return, self.ep_len)
 
+    def step_range(self, first: int, count: int, actions: torch.Tensor, stream: torch.cuda.Stream | None = None) -> None:
+        """Step envs [first, first + count) only (first a multiple of 32); `actions` is the f32[count,4] slice for them.  Results
+        land in the same rows of the persistent output buffers.  Ordered on `stream` (default: the current stream) -- sub-ranges
+        on different streams run independently, which is what QuadVecEnv's chunked host pipeline uses."""
+        if actions.dtype != torch.float32 or tuple(actions.shape) != (count, 4) or not actions.is_contiguous():
+            raise ValueError(f"actions must be contiguous float32[{count},4]")
+        sl = slice(first, first + count)
+        p = lambda t: C.c_void_p(t[sl].data_ptr())
+        st = C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+        check(self.lib, self._h,
+              self.lib.qs_step_range(self._h, first, count, C.c_void_p(actions.data_ptr()), p(self.obs), p(self.reward), p(self.flags),
+                                     p(self.terminal_obs), p(self.ep_return), p(self.ep_len), st), "qs_step_range")
+
     def fuse_obs_moments(self, moments: torch.Tensor | None, shift_stats: torch.Tensor | None = None,
                          merge_stats: torch.Tensor | None = None) -> None:
         """From now on every step() also writes (n, mean[D], M2[D]) of the returned observations into `moments` (f64[1+2D]):

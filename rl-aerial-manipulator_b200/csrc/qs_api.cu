@@ -173,6 +173,8 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     h->mom_out = nullptr;
     h->mom_stats = nullptr;
     h->mom_merge = nullptr;
+    h->range_first = 0;
+    h->range_count = 0;
     h->ls_tables = nullptr;
     h->ls_counters = nullptr;
     h->ls_steps = nullptr;
@@ -238,6 +240,23 @@ int qs_step(qs_handle* h, const float* actions, float* obs_out, void* reward_out
         rc = launch_step_f64(h, actions, obs_out, (double*)reward_out, flags_out, terminal_obs_out, (double*)ep_return_out, ep_len_out, (cudaStream_t)stream);
     else
         rc = launch_step_lsoda(h, actions, obs_out, (double*)reward_out, flags_out, terminal_obs_out, (double*)ep_return_out, ep_len_out, (cudaStream_t)stream);
+    return rc;
+}
+
+int qs_step_range(qs_handle* h, int64_t first_env, int64_t count, const float* actions, float* obs_out, void* reward_out,
+                  uint8_t* flags_out, float* terminal_obs_out, void* ep_return_out, int32_t* ep_len_out, void* stream) {
+    if (!h) { set_error(nullptr, "qs_step_range: null handle"); return QS_EINVAL; }
+    if (first_env < 0 || count < 1 || (first_env & 31) || first_env + count > h->cfg.n_envs) {
+        set_error(h, "qs_step_range: need 0 <= first_env (multiple of 32), count >= 1, first_env + count <= n_envs");
+        return QS_EINVAL;
+    }
+    if (h->cfg.integrator != QS_RK4) { set_error(h, "qs_step_range: RK4 handles only"); return QS_EINVAL; }
+    if (h->mom_out) { set_error(h, "qs_step_range: not available while qs_step_moments is armed"); return QS_EINVAL; }
+    h->range_first = first_env;
+    h->range_count = count;
+    const int rc = qs_step(h, actions, obs_out, reward_out, flags_out, terminal_obs_out, ep_return_out, ep_len_out, stream);
+    h->range_first = 0;
+    h->range_count = 0;
     return rc;
 }
 

@@ -16,6 +16,7 @@ struct qs_handle {
     qs::LsodaTables* ls_tables;
     int32_t* ls_counters;
     double* ls_steps;
+    int64_t range_first, range_count;   // qs_step_range: the sub-range the next launch covers (count 0 = all envs)
     int num_sms;
     bool initialized;
     char error[512];
@@ -41,6 +42,12 @@ inline StepParams<Real> base_params(const qs_handle* h) {
     StepParams<Real> p;
     p.pool = h->pool;
     p.n = c.n_envs;
+    p.env_id_offset = c.env_id_offset;
+    if (h->range_count > 0) {   // a sub-range of whole warp tiles: the tile-major pool makes it a plain pointer offset
+        p.pool = static_cast<unsigned char*>(h->pool) + (h->range_first / 32) * (h->bytes_per_env * 32);
+        p.n = h->range_count;
+        p.env_id_offset = c.env_id_offset + h->range_first;
+    }
     p.mom_partial = h->mom_out ? h->mom_scratch : nullptr;
     p.mom_stats = h->mom_stats;
     p.mom_prev = h->mom_out;
@@ -52,7 +59,6 @@ inline StepParams<Real> base_params(const qs_handle* h) {
     p.scale_f32 = c.action_scale_f32;
     p.auto_reset = c.auto_reset;
     p.seed = c.seed;
-    p.env_id_offset = c.env_id_offset;
     p.rtol = c.lsoda_rtol;
     p.atol = c.lsoda_atol;
     Model<Real>& m = p.model;
@@ -91,7 +97,7 @@ inline unsigned step_grid(const qs_handle* h, Kernel k, int block) {
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, 0);
     if (per_sm < 1) per_sm = 1;
-    const int64_t need = (h->cfg.n_envs + block - 1) / block;
+    const int64_t need = ((h->range_count > 0 ? h->range_count : h->cfg.n_envs) + block - 1) / block;
     const int64_t cap = (int64_t)per_sm * h->num_sms;
     return (unsigned)(need < cap ? need : cap);
 }

@@ -127,9 +127,26 @@ class MlpPolicyKernel:
             raise RuntimeError(f"qs_policy_forward failed ({rc}): {self.lib.qs_policy_last_error().decode()}")
         return self.actions, self.values, self.logp
 
-    def predict_host(self, obs_np: np.ndarray, stochastic: bool = False, norm_stats=None) -> np.ndarray:
-        """model.predict for a host batch: obs H2D (pinned) -> fused forward -> clipped actions D2H."""
+    def _forward_range(self, first: int, count: int, obs, noise, norm_stats, stream) -> None:
+        """forward() on rows [first, first + count) of already allocated full-size buffers, ordered on `stream`."""
+        sl = slice(first, first + count)
+        p = lambda t: C.c_void_p(t[sl].data_ptr()) if t is not None else None
+        rc = self.lib.qs_policy_forward(C.c_void_p(self.params.data_ptr()), self.obs_dim, p(obs), p(noise), count,
+                                        C.c_void_p(norm_stats.data_ptr()) if norm_stats is not None else None, 1e-8, 10.0, None,
+                                        p(self.actions), p(self.actions_clipped), C.byref(self._lo), C.byref(self._hi),
+                                        p(self.values), p(self.logp), self.impl, C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"qs_policy_forward failed ({rc}): {self.lib.qs_policy_last_error().decode()}")
+
+    def predict_host(self, obs_np: np.ndarray, stochastic: bool = False, norm_stats=None, pipeline_chunks: int | None = None) -> np.ndarray:
+        """model.predict for a host batch: obs H2D (pinned) -> fused forward -> clipped actions D2H.  From 262,144 rows the batch
+        goes through in 4 chunks on separate streams (pipeline_chunks), so observations of chunk c+1 are copied up while chunk c
+        is evaluated and its actions come down."""
         n = obs_np.shape[0]
+        if pipeline_chunks is None:
+            pipeline_chunks = 4 if n >= 262144 else 1
+        if pipeline_chunks > 1:
+            return self._predict_host_chunked(obs_np, stochastic, norm_stats, pipeline_chunks)
         if self._host is None or self._host[0].shape[0] != n:
             self._host = (torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory(),
                           torch.empty((n, NACT), dtype=torch.float32).pin_memory(),
@@ -145,6 +162,38 @@ class MlpPolicyKernel:
         self.forward(d_obs, noise, norm_stats=norm_stats)
         h_act.copy_(self.actions_clipped, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        return h_act.numpy()
+
+    def _predict_host_chunked(self, obs_np, stochastic, norm_stats, chunks) -> np.ndarray:
+        n = obs_np.shape[0]
+        if self._host is None or self._host[0].shape[0] != n:
+            self._host = (torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory(),
+                          torch.empty((n, NACT), dtype=torch.float32).pin_memory(),
+                          torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device),
+                          torch.Generator(device=self.device).manual_seed(0))
+        if getattr(self, "_chunk_streams", None) is None or len(self._chunk_streams) != chunks:
+            self._chunk_streams = [torch.cuda.Stream(device=self.device) for _ in range(chunks)]
+        h_obs, h_act, d_obs, gen = self._host
+        src = torch.from_numpy(np.ascontiguousarray(obs_np, dtype=np.float32))
+        if not src.is_pinned():
+            h_obs.numpy()[...] = obs_np
+            src = h_obs
+        self._ensure(n)
+        cur = torch.cuda.current_stream(self.device)
+        noise = torch.randn((n, NACT), device=self.device, generator=gen) if stochastic else None
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        per = ((n + chunks - 1) // chunks + 127) // 128 * 128
+        for st, f in zip(self._chunk_streams, range(0, n, per)):
+            c = min(per, n - f)
+            sl = slice(f, f + c)
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                d_obs[sl].copy_(src[sl], non_blocking=True)
+                self._forward_range(f, c, d_obs, noise, norm_stats, st)
+                h_act[sl].copy_(self.actions_clipped[sl], non_blocking=True)
+        for st in self._chunk_streams:
+            st.synchronize()
         return h_act.numpy()
 
     # ---- plain torch reference (tests only use it as the fp32 checker) ------------------------------

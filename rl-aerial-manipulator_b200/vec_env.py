@@ -112,7 +112,11 @@ class QuadVecEnv(_SB3VecEnv):
 
     def __init__(self, num_envs: int = 8, env_version: int = 2, precision: str = "f32", integrator: str = "rk4",
                  substeps: int = 1, obs_scaled: bool = True, device: int | None = None, seed: int = 0,
-                 env_id_offset: int = 0, monitor: bool = True, info_mode: str = "dict", v2_random_waypoints: bool = False):
+                 env_id_offset: int = 0, monitor: bool = True, info_mode: str = "dict", v2_random_waypoints: bool = False,
+                 pipeline_chunks: int | None = None):
+        """pipeline_chunks: split a step into this many env sub-ranges, each on its own stream -- actions of chunk c+1 are copied
+        up while chunk c steps and its observations come down, so the PCIe link works in both directions at once.
+        None: 4 from 262,144 envs, else 1."""
         self.sim = BatchedQuadEnv(num_envs, env_version=env_version, precision=precision, integrator=integrator,
                                   substeps=substeps, obs_scaled=obs_scaled, auto_reset=True, device=device,
                                   env_id_offset=env_id_offset, seed=seed, v2_random_waypoints=v2_random_waypoints)
@@ -142,6 +146,13 @@ class QuadVecEnv(_SB3VecEnv):
         self._h_obs, self._h_reward, self._h_flags = self._h_bufs[0]
         self._pending = False
         self._transform = None      # optional device-side post-processing of a step (QuadVecNormalize installs one)
+        if pipeline_chunks is None:
+            pipeline_chunks = 4 if (n >= 262144 and integrator == "rk4") else 1
+        self._chunks = []           # (first, count) sub-ranges of whole warp tiles
+        if pipeline_chunks > 1:
+            per = ((n + pipeline_chunks - 1) // pipeline_chunks + 31) // 32 * 32
+            self._chunks = [(f, min(per, n - f)) for f in range(0, n, per)]
+            self._chunk_streams = [torch.cuda.Stream(device=self.sim.device) for _ in self._chunks]
         self.h2d_bytes_per_step = n * 4 * 4
         self.d2h_bytes_per_step = n * d * 4 + n * self._h_reward.element_size() + n
 
@@ -162,6 +173,18 @@ class QuadVecEnv(_SB3VecEnv):
             src = self._h_actions
         self._flip ^= 1
         self._h_obs, self._h_reward, self._h_flags = self._h_bufs[self._flip]
+        if len(self._chunks) > 1 and self._transform is None:
+            sim = self.sim
+            for (f, c), st in zip(self._chunks, self._chunk_streams):
+                sl = slice(f, f + c)
+                with torch.cuda.stream(st):
+                    self._d_actions[sl].copy_(src[sl], non_blocking=True)
+                    sim.step_range(f, c, self._d_actions[sl], st)
+                    self._h_obs[sl].copy_(sim.obs[sl], non_blocking=True)
+                    self._h_reward[sl].copy_(sim.reward[sl], non_blocking=True)
+                    self._h_flags[sl].copy_(sim.flags[sl], non_blocking=True)
+            self._pending = True
+            return
         with torch.cuda.stream(self._stream):
             self._d_actions.copy_(src, non_blocking=True)
             out = self.sim.step(self._d_actions)
@@ -173,6 +196,9 @@ class QuadVecEnv(_SB3VecEnv):
 
     def step_wait(self):
         assert self._pending, "step_wait() without step_async()"
+        if len(self._chunks) > 1 and self._transform is None:
+            for st in self._chunk_streams:
+                st.synchronize()
         self._stream.synchronize()
         self._pending = False
         obs = self._h_obs.numpy()

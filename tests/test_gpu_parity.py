@@ -572,3 +572,31 @@ def test_tma_pipeline_kernel_matches_default_kernel():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1], outs
+
+
+def test_chunked_host_pipeline_equals_single_launch(golden_dir):
+    """QuadVecEnv(pipeline_chunks=4) (qs_step_range on four streams) and predict_host(pipeline_chunks=4) return exactly what the
+    single-launch paths return: sub-ranges of whole warp tiles are independent."""
+    from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+    from rl_aerial_manipulator_b200.vec_env import QuadVecEnv
+    n = 10_000 + 37                                              # ragged: last chunk and last tile partially filled
+    a = QuadVecEnv(n, env_version=2, seed=8, pipeline_chunks=1, info_mode="lazy")
+    b = QuadVecEnv(n, env_version=2, seed=8, pipeline_chunks=4, info_mode="lazy")
+    assert len(b._chunks) == 4 and all(f % 32 == 0 for f, _ in b._chunks) and sum(c for _, c in b._chunks) == n
+    oa, ob = a.reset(), b.reset()
+    np.testing.assert_array_equal(oa, ob)
+    rng = np.random.default_rng(0)
+    pol = MlpPolicyKernel.from_npz(os.path.join(golden_dir, "policy_v2.npz"), device="cuda", impl="tensor")
+    for t in range(160):
+        act = (np.array([0, -1, -1, -1.0]) + np.array([0.4, 2, 2, 2.0]) * rng.random((n, 4))).astype(np.float32)
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act)
+        np.testing.assert_array_equal(oa, ob)
+        np.testing.assert_array_equal(ra, rb)
+        np.testing.assert_array_equal(da, db)
+    assert da.sum() >= 0 and int(a.sim.get_state(["episode"])["episode"].sum()) > 0       # some envs crashed and were reset
+    p1 = pol.predict_host(oa, stochastic=False, pipeline_chunks=1).copy()
+    p4 = pol.predict_host(oa, stochastic=False, pipeline_chunks=4).copy()
+    np.testing.assert_array_equal(p1, p4)
+    a.close()
+    b.close()

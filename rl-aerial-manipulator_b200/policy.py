@@ -11,6 +11,7 @@ mlp_extractor.{policy_net,value_net}.{0,2,4}, action_net, value_net, log_std).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import io
 import zipfile
 
@@ -144,7 +145,7 @@ class MlpPolicyKernel:
         is evaluated and its actions come down."""
         n = obs_np.shape[0]
         if pipeline_chunks is None:
-            pipeline_chunks = 4 if n >= 262144 else 1
+            pipeline_chunks = int(os.environ.get("QS_PIPELINE_CHUNKS", "4")) if n >= 262144 else 1
         if pipeline_chunks > 1:
             return self._predict_host_chunked(obs_np, stochastic, norm_stats, pipeline_chunks)
         if self._host is None or self._host[0].shape[0] != n:

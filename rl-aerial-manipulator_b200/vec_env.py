@@ -18,6 +18,7 @@ more than the step).  The zero-copy path is BatchedQuadEnv.
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Any, Sequence
 
@@ -147,7 +148,7 @@ class QuadVecEnv(_SB3VecEnv):
         self._pending = False
         self._transform = None      # optional device-side post-processing of a step (QuadVecNormalize installs one)
         if pipeline_chunks is None:
-            pipeline_chunks = 4 if (n >= 262144 and integrator == "rk4") else 1
+            pipeline_chunks = int(os.environ.get("QS_PIPELINE_CHUNKS", "4")) if (n >= 262144 and integrator == "rk4") else 1
         self._chunks = []           # (first, count) sub-ranges of whole warp tiles
         if pipeline_chunks > 1:
             per = ((n + pipeline_chunks - 1) // pipeline_chunks + 31) // 32 * 32

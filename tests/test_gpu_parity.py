@@ -600,3 +600,49 @@ def test_chunked_host_pipeline_equals_single_launch(golden_dir):
     np.testing.assert_array_equal(p1, p4)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 1013, 4097])
+def test_no_writes_past_the_batch_end(golden_dir, n):
+    """Ragged batch sizes with guard rows behind every output buffer (the pool's sanitizer is not available): the step kernels,
+    the reset kernel and the three policy kernels must leave the rows past n untouched."""
+    from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+    guard = 96
+    sentinel = 1234.5
+
+    def guarded(shape, dtype):
+        big = torch.full((shape[0] + guard, *shape[1:]), sentinel if dtype.is_floating_point else 77, dtype=dtype, device="cuda")
+        return big, big[: shape[0]]
+
+    for variant, prec in (("v2", "f32"), ("v1", "f32"), ("v2", "f64"), ("v2m", "f32")):
+        env = make_env(n, variant, precision=prec, seed=3)
+        bigs = {}
+        for name in ("obs", "reward", "flags", "terminal_obs", "ep_return", "ep_len"):
+            t = getattr(env, name)
+            bigs[name], view = guarded(tuple(t.shape), t.dtype)
+            setattr(env, name, view)
+        env.reset()
+        for t in range(3):
+            env.step(torch.rand((n, 4), device="cuda"))
+        for name, big in bigs.items():
+            tail = big[n:]
+            want = sentinel if big.dtype.is_floating_point else 77
+            assert bool((tail == want).all()), (variant, prec, name)
+        assert torch.isfinite(env.obs).all()
+        env.close()
+    for impl in ("fp32", "tensor", "tensor_fast"):
+        pol = MlpPolicyKernel.from_npz(os.path.join(golden_dir, "policy_v2.npz"), device="cuda", impl=impl)
+        pol._ensure(n)
+        bigs = {}
+        for name in ("actions", "actions_clipped", "values", "logp"):
+            t = getattr(pol, name)
+            bigs[name], view = guarded(tuple(t.shape), t.dtype)
+            setattr(pol, name, view)
+        obs = torch.randn((n, 20), device="cuda")
+        big_norm, norm_out = guarded((n, 20), torch.float32)
+        stats = torch.zeros(41, dtype=torch.float64, device="cuda"); stats[0] = 1.0; stats[21:] = 1.0
+        pol.forward(obs, torch.randn((n, 4), device="cuda"), norm_stats=stats, obs_norm_out=norm_out)
+        torch.cuda.synchronize()
+        for name, big in {**bigs, "obs_norm_out": big_norm}.items():
+            assert bool((big[n:] == sentinel).all()), (impl, name)
+        assert torch.isfinite(pol.actions).all() and torch.isfinite(norm_out).all()

@@ -133,6 +133,18 @@ __global__ void __launch_bounds__(STEP_BLOCK, StepOcc<Real, INTEG>::MINB) env_st
                 a_nx = __ldcs(reinterpret_cast<const float4*>(p.actions) + en);
             }
         }
+#ifdef QS_STEP_L2_PREFETCH          // A/B: no register prefetch, but the next tile's record and actions are pulled into L2
+        if (!PREFETCH) {
+            using L = PoolLayout<Real, VER>;
+            const int64_t wn = wt + warps_total;
+            if (wn < n_warp_tiles) {
+                constexpr int LINES = (L::TILE_BYTES + 127) / 128;
+                const unsigned char* rec = reinterpret_cast<const unsigned char*>(p.pool) + wn * (int64_t)L::TILE_BYTES;
+                for (int l = lane; l < LINES; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + l * 128));
+                if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(p.actions + wn * 128) + lane * 128));
+            }
+        }
+#endif
         if (live) {
             if (!PREFETCH) {
                 pool_load<Real, VER>(p.pool, p.n, e, s);

@@ -219,3 +219,72 @@ def test_euler_matches_oracle(hh):
         hh.lib.hh_rpy(qi.ctypes.data_as(C.c_void_p), out[i].ctypes.data_as(C.c_void_p))
     r, p, y = qo.quat_to_rpy(q[:, 0], q[:, 1], q[:, 2], q[:, 3])
     np.testing.assert_allclose(out, np.stack([r, p, y], 1), rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1", "v2m"])
+def test_randomised_states_step_matches_oracle(hh, variant):
+    """Differential test beyond the golden cases: 1,500 random internal states per variant -- waypoint lists of every length,
+    counters and step counts at and around their limits, positions on both sides of the reach / crash / bounds thresholds,
+    first-step states -- through the device code (float64, RK4 x 2) and through the oracle: flags, counters and waypoint
+    bookkeeping exact, reward and state to 1e-11."""
+    rng = np.random.default_rng({"v2": 1, "v1": 2, "v2m": 3}[variant])
+    oname = "v1" if variant == "v1" else "v2"
+    ver = {"v2": 2, "v1": 1, "v2m": 3}[variant]
+    n = 1500
+    kmax = {"v2": 1, "v1": 2, "v2m": 3}[variant]
+    b = qo.EnvBatch.empty(oname, n, max_wp=3)
+    b.n_wp[:] = rng.integers(1, kmax + 1, n)
+    b.wp_list[:] = np.stack([rng.uniform(-1, 1, (n, 3)), rng.uniform(-1, 1, (n, 3)), rng.uniform(0.3, 3, (n, 3))], -1)
+    b.wp_index[:] = np.minimum(rng.integers(0, 3, n), b.n_wp - (rng.random(n) < 0.5))      # some already past the last entry
+    b.wp_index[:] = np.clip(b.wp_index, 0, b.n_wp)
+    ar = np.arange(n)
+    b.cur_wp = b.wp_list[ar, np.minimum(b.wp_index, b.n_wp - 1)].copy()
+    b.y[:] = 0
+    # position: a third right around the 0.1 m reach sphere, a few near the ground / far away, the rest anywhere
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.where(rng.random(n) < 0.35, rng.uniform(0.09, 0.11, n), rng.uniform(0.0, 2.5, n))
+    b.y[:, 0:3] = b.cur_wp + d * r[:, None]
+    low = rng.random(n) < 0.08
+    b.y[low, 2] = rng.uniform(0.09, 0.11, low.sum())
+    far = rng.random(n) < 0.04
+    b.y[far, 0] = rng.choice([-1, 1], far.sum()) * rng.uniform(9.9, 10.1, far.sum())
+    b.y[:, 3:6] = rng.normal(size=(n, 3)) * np.where(rng.random(n) < 0.3, 0.05, 1.0)[:, None]
+    q = rng.normal(size=(n, 4)) * 0.3 + [1, 0, 0, 0]
+    b.y[:, 6:10] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    b.y[:, 10:13] = rng.normal(size=(n, 3)) * np.where(rng.random(n) < 0.3, 0.05, 1.5)[:, None]
+    b.last_distance[:] = np.where(rng.random(n) < 0.1, np.nan, np.linalg.norm(b.y[:, 0:3] - b.cur_wp, axis=1) + rng.normal(size=n) * 0.01)
+    limit = qo.MAX_STEPS[oname]
+    b.current_step[:] = np.where(rng.random(n) < 0.3, limit + rng.integers(-2, 2, n), rng.integers(0, limit, n))
+    if oname == "v2":
+        b.final_reached[:] = (b.wp_index >= b.n_wp) & (rng.random(n) < 0.9)
+        b.wp_index[:] = np.where(b.final_reached, b.n_wp, np.minimum(b.wp_index, b.n_wp - 1))
+        b.cur_wp = b.wp_list[ar, np.minimum(b.wp_index, b.n_wp - 1)].copy()
+        b.counter[:] = np.where(b.final_reached, np.where(rng.random(n) < 0.5, 500 + rng.integers(-2, 3, n), rng.integers(0, 500, n)), 0)
+        b.final_yaw[:] = rng.uniform(-np.pi, np.pi, n)
+    else:
+        b.wp_index[:] = np.minimum(b.wp_index, b.n_wp - 1)
+        b.cur_wp = b.wp_list[ar, b.wp_index].copy()
+    act = np.stack([rng.uniform(0, 2, n), *rng.uniform(-1, 1, (3, n))], 1).astype(np.float32)
+    pre = b.copy()
+    with np.errstate(all="ignore"):
+        obs_o, rew_o, term_o, trunc_o, info_o = qo.step(b, act, integrator="rk4", substeps=2)
+    seen = set()
+    for i in range(n):
+        st = dict(y=pre.y[i], wp_list=pre.wp_list[i], n_wp=int(pre.n_wp[i]), wp_index=int(pre.wp_index[i]),
+                  last_distance=float(pre.last_distance[i]), current_step=int(pre.current_step[i]), counter=int(pre.counter[i]),
+                  final_reached=bool(pre.final_reached[i]), final_yaw=float(pre.final_yaw[i]))
+        out, obs, rew, flags, ep_len, _ = hh.step(ver, st, act[i], f32=False, integ="rk4", substeps=2)
+        want = int(term_o[i]) | int(trunc_o[i]) << 1 | (int(info_o[i]) & 0xF) << 2
+        # a state exactly on a threshold may round to either side in the two implementations' last bit: none is expected, but
+        # say so if it happens instead of failing on a measure-zero tie
+        dist = np.linalg.norm(b.y[i, 0:3] - pre.cur_wp[i])
+        tie = min(abs(dist - 0.1), abs(dist - 0.5), abs(b.y[i, 2] - 0.1), abs(np.linalg.norm(b.y[i, 0:3]) - 10)) < 1e-12
+        assert flags == want or tie, (i, flags, want)
+        np.testing.assert_allclose(out["y"], b.y[i], rtol=1e-12, atol=1e-13)
+        assert out["wp_index"] == min(int(b.wp_index[i]), 3) and out["current_step"] == b.current_step[i]
+        if oname == "v2":
+            assert out["counter"] == b.counter[i] and out["final_reached"] == bool(b.final_reached[i])
+        np.testing.assert_allclose(rew, rew_o[i], rtol=1e-11, atol=1e-10)
+        np.testing.assert_allclose(obs, obs_o[i], rtol=2e-7, atol=1e-12)
+        seen.add(want)
+    assert len(seen) >= (6 if oname == "v2" else 5), seen          # plain, truncated, success(+stopped), crashed, out of bounds ...

@@ -84,3 +84,23 @@ def mlp_policy_forward(sd, obs, noise=None, dtype=np.float64):
     actions = mean + np.exp(log_std) * eps
     logp = np.sum(-0.5 * eps ** 2 - log_std - 0.5 * np.log(2 * np.pi), axis=1)
     return actions, value, logp, mean
+
+
+def merge_moments(stats, moments):
+    """CPU restatement of qs_vecnorm_merge / qs_xchg_merge (RunningMeanStd.update_from_moments applied to k batch triplets in rank
+    order) for float64 torch CPU tensors: stats (count, mean[d], var[d]) <- merge of triplets (n, mean[d], M2[d]).
+    Test infrastructure: the world-size-2 gloo test of the moment exchange uses it as the checker."""
+    import torch
+    d = (stats.shape[0] - 1) // 2
+    count, mean, var = stats[0].clone(), stats[1:1 + d].clone(), stats[1 + d:].clone()
+    for m in moments.reshape(-1, 1 + 2 * d):
+        bn = m[0]
+        if bn <= 0:
+            continue
+        delta = m[1:1 + d] - mean
+        tot = count + bn
+        mean = mean + delta * bn / tot
+        M2 = var * count + m[1 + d:] + delta * delta * count * bn / tot
+        var = M2 / tot
+        count = tot
+    return torch.cat([count.reshape(1), mean, var])

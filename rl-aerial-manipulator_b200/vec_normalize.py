@@ -44,24 +44,6 @@ def _bind(lib):
     lib._vn_bound = True
 
 
-def merge_moments(stats, moments):
-    """Host restatement of qs_vecnorm_merge / RunningMeanStd.update_from_moments for float64 numpy or torch
-    CPU tensors: stats (count, mean[d], var[d]) <- merge of triplets (n, mean[d], M2[d]).  Used by the gloo tests."""
-    d = (stats.shape[0] - 1) // 2
-    count, mean, var = stats[0].clone(), stats[1:1 + d].clone(), stats[1 + d:].clone()
-    for m in moments.reshape(-1, 1 + 2 * d):
-        bn = m[0]
-        if bn <= 0:
-            continue
-        delta = m[1:1 + d] - mean
-        tot = count + bn
-        mean = mean + delta * bn / tot
-        M2 = var * count + m[1 + d:] + delta * delta * count * bn / tot
-        var = M2 / tot
-        count = tot
-    return torch.cat([count.reshape(1), mean, var])
-
-
 class DeviceRunningMeanStd:
     """stable_baselines3.common.running_mean_std.RunningMeanStd on the device."""
 

@@ -89,7 +89,7 @@ def _np_moments(x):
 
 
 def test_merge_of_shards_equals_one_shot():
-    from rl_aerial_manipulator_b200.vec_normalize import merge_moments
+    from oracle.sb3_oracle import merge_moments
     rng = np.random.default_rng(0)
     x = (rng.normal(size=(4000, 20)) * 3 + 2).astype(np.float32)
     ref = so.RunningMeanStd((20,))
@@ -106,7 +106,7 @@ def test_merge_of_shards_equals_one_shot():
 
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
-    from rl_aerial_manipulator_b200.vec_normalize import merge_moments
+    from oracle.sb3_oracle import merge_moments
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     rng = np.random.default_rng(42)
     x = (rng.normal(size=(1024, 17)) * 2 - 1).astype(np.float32)           # the global batch, same on every rank

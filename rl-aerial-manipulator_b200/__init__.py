@@ -2,7 +2,7 @@
 
 Import as `rl_aerial_manipulator_b200` (alias module at the repo root).
 """
-from . import params  # noqa: F401
+from .quad_constants import QUAD  # noqa: F401
 from ._cabi import make_config, load_library, QuadsimError  # noqa: F401
 
-__all__ = ["params", "make_config", "load_library", "QuadsimError"]
+__all__ = ["QUAD", "make_config", "load_library", "QuadsimError"]

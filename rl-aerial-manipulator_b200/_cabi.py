@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-from . import params
+from .quad_constants import QUAD
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QS_LIB_PATH") or os.path.join(HERE, "lib", "libquadsim.so")
@@ -49,7 +49,7 @@ class QsStateView(C.Structure):
 
 def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", substeps=1, obs_scaled=True,
                 action_scale_f32=True, auto_reset=True, device=0, env_id_offset=0, seed=0, v2_random_waypoints=False) -> QsConfig:
-    """qs_config with the reference's model constants (params.py) and NumPy-evaluated trig tables."""
+    """qs_config with the reference's model constants (quad_constants.QUAD) and NumPy-evaluated trig tables."""
     c = QsConfig()
     c.abi_version = QS_ABI_VERSION
     c.env_version = int(env_version)
@@ -64,13 +64,13 @@ def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", subs
     c.n_envs = int(n_envs)
     c.env_id_offset = int(env_id_offset)
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    c.mass, c.g, c.dt = params.mass, params.g, params.dt
-    c.inertia[:] = params.I.reshape(-1).tolist()
-    c.inv_inertia[:] = params.invI.reshape(-1).tolist()
-    c.mix[:] = params.A.reshape(-1).tolist()
-    c.inv_mix[:] = params.invA.reshape(-1).tolist()
-    c.max_prop_thrust = params.maxF / 4
-    c.min_prop_thrust = params.minF / 4
+    c.mass, c.g, c.dt = QUAD.mass, QUAD.gravity, QUAD.control_dt
+    c.inertia[:] = QUAD.inertia.reshape(-1).tolist()
+    c.inv_inertia[:] = QUAD.inv_inertia.reshape(-1).tolist()
+    c.mix[:] = QUAD.mixer.reshape(-1).tolist()
+    c.inv_mix[:] = QUAD.inv_mixer.reshape(-1).tolist()
+    c.max_prop_thrust = QUAD.max_total_thrust / 4
+    c.min_prop_thrust = QUAD.min_total_thrust / 4
     # v2 trajectory generators (utils2/utils.py:41,84-85): sin(2*t*pi), t = j/K, and cos/sin((j/K) * 2*pi*turns), turns = 1, evaluated
     # with the reference's own NumPy expressions for K = 1 (as shipped, rl_env_scaledObs.py:47) and K = 2, 3 (the :46 alternative)
     for k in (1, 2, 3):
@@ -79,7 +79,7 @@ def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", subs
             c.sin_tab[k * (k - 1) // 2 + j - 1] = float(np.sin(2 * t * np.pi))
             c.cos_tab[k * (k - 1) // 2 + j - 1] = float(np.cos((j / k) * (2 * np.pi * 1)))
             assert np.sin(2 * t * np.pi) == np.sin((j / k) * (2 * np.pi * 1))     # one angle per (K, j): the helix shares the sine
-    c.lsoda_rtol = c.lsoda_atol = params.ODEINT_TOL
+    c.lsoda_rtol = c.lsoda_atol = QUAD.odeint_tol
     return c
 
 

@@ -18,7 +18,7 @@ import math
 import numpy as np
 import torch
 
-from . import params
+from .quad_constants import QUAD
 from .batched_env import BatchedQuadEnv
 from .vec_env import _box
 
@@ -57,7 +57,7 @@ class QuadcopterView:
     def world_frame(self) -> np.ndarray:
         """3x6 world coordinates of the four motors, the origin and the hub top (quadcopter.py:40-51)."""
         wHb = np.r_[np.c_[self.rotation_matrix(), self.state[0:3]], np.array([[0, 0, 0, 1]])]
-        return wHb.dot(params.body_frame.T)[0:3]
+        return wHb.dot(QUAD.body_frame.T)[0:3]
 
 
 class WaypointQuadEnv:
@@ -120,7 +120,7 @@ class WaypointQuadEnv:
 
     def step(self, action):
         a = np.asarray(action, dtype=np.float32).reshape(4)
-        self.F = a[0] * np.float32(params.mass) * np.float32(params.g)     # float32 arithmetic, like the reference under NumPy >= 2
+        self.F = a[0] * np.float32(QUAD.mass) * np.float32(QUAD.gravity)     # float32 arithmetic, like the reference under NumPy >= 2
         self.M = a[1:4] * np.float32(0.1)
         self._act.copy_(torch.from_numpy(a).reshape(1, 4))
         out = self._sim.step(self._act)

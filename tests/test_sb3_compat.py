@@ -68,7 +68,7 @@ def test_policy_zip_writer(tmp_path, golden_dir):
 
 def test_quadcopter_view_matches_reference_formulas():
     from rl_aerial_manipulator_b200.gym_env import QuadcopterView
-    from rl_aerial_manipulator_b200 import params
+    from rl_aerial_manipulator_b200 import QUAD
     rng = np.random.default_rng(0)
     q = QuadcopterView()
     for _ in range(20):
@@ -87,7 +87,7 @@ def test_quadcopter_view_matches_reference_formulas():
         wf = q.world_frame()
         assert wf.shape == (3, 6)
         np.testing.assert_allclose(wf[:, 4], q.state[0:3], atol=1e-12)                       # origin column
-        np.testing.assert_allclose(np.linalg.norm(wf[:, 0] - wf[:, 4]), params.arm_length, atol=1e-12)
+        np.testing.assert_allclose(np.linalg.norm(wf[:, 0] - wf[:, 4]), QUAD.arm_length, atol=1e-12)
 
 
 @pytest.mark.gpu

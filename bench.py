@@ -5,16 +5,19 @@
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over the whole env batch.  Workloads (BASELINE.json `configs`):
-  rollout  configs[3]/[4]: v2 env, 1,048,576 envs per GPU, float32: MlpPolicy rollout forward (weights of the
-           reference's checkpoints_from_8_6M/ppo_model_2300000_steps.zip) -> sample -> clip -> env step
-           (physics + reward + termination + obs) -> auto-reset.  Default.
+  rollout  configs[3]/[4]: v2 env, 1,048,576 envs per GPU, float32: VecNormalize statistics (moments reduced inside the step
+           kernel) -> MlpPolicy rollout forward on tcgen05 (weights of the reference's
+           checkpoints_from_8_6M/ppo_model_2300000_steps.zip; normalise, sample, clip fused) -> env step (physics + reward +
+           termination + obs) -> auto-reset.  Default.
   step     configs[2]-style: the env step alone on pre-generated uniform-random actions.
-Envs are independent, so N GPUs run N shards with no data-path collective (weak scaling); the only
-collective is the max-over-ranks of the timing.
+Envs are independent, so N GPUs run N shards with no data-path collective (weak scaling); the only exchange is the
+VecNormalize moment triplet (41 doubles per rank and step: one fused all-gather+merge kernel over NVLink peer memory, NCCL
+as fallback) and the max-over-ranks of the timing.
 
-Printed JSON (one line, rank 0): the base contract + `roofline` (dominant kernel vs measured HBM peak),
-`cpu_baseline` (the CPU oracle port of the reference step on the host cores), `e2e` (same metric through
-the SB3-style VecEnv call with pinned host buffers, copies inside the timed region), `clocks`.
+Printed JSON (one line, rank 0): the base contract + `roofline` (dominant kernel: the policy forward against the measured
+tensor peak; `roofline_other`: the HBM-bound env step), `cpu_baseline` (the CPU oracle port of the reference step on the host
+cores), `e2e` (same metric through the SB3-style VecEnv / predict calls with pinned host buffers, copies inside the timed
+region), `gpu_launches`, `clocks`.
 """
 from __future__ import annotations
 

@@ -282,6 +282,7 @@ def run_gpu(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()                                                # ranks enter the first exchange together
     for i in range(args.warmup):
         one_step(i)
     barrier()

@@ -244,7 +244,7 @@ const char* qs_gae_last_error(void);
  * all ranks, no NCCL call, one launch, safe to capture in a CUDA graph (the sequence number lives on the device).
  * Setup: every rank calls qs_xchg_create (allocates its buffer, returns a 64-byte CUDA IPC handle), the ranks exchange the
  * handles by any host channel (torch.distributed.all_gather_object), then qs_xchg_connect maps the peers' buffers.
- * All ranks must call qs_xchg_merge the same number of times; a rank that waits longer than ~2 s on a peer gives up, sets a
+ * All ranks must call qs_xchg_merge the same number of times; a rank that waits longer than ~10 s on a peer gives up, sets a
  * sticky error (qs_xchg_failed() != 0) and merges what has arrived, so a dead peer cannot hang the GPU.
  * The NCCL path (all_gather_into_tensor + qs_vecnorm_merge) stays available and is the one the gloo CPU tests cover.
  */

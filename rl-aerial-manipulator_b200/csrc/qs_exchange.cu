@@ -7,7 +7,7 @@
 // Step s (1, 2, ...; the counter lives in device memory so a captured graph replays correctly), parity p = s & 1:
 //   1. thread c < len stores local[c] into slots[p][rank][c] of EVERY rank's buffer (its own included), then fences system-wide;
 //   2. one thread publishes flags[p][rank] = s in every buffer (after the CTA barrier, so all data stores are fenced);
-//   3. every thread acquire-spins until its own buffer's flags[p][q] >= s for all q (bounded: ~2 s, then a sticky error);
+//   3. every thread acquire-spins until its own buffer's flags[p][q] >= s for all q (bounded: ~10 s, then a sticky error);
 //   4. Chan merge of slots[p][0..world) in rank order into the running statistics.
 // Two parities suffice: a rank can only reach step s+2 after every rank has published step s+1, which each rank does after it
 // finished reading step s.
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) xchg_merge_kernel(void* const* __restrict
     const long long t0 = clock64();
     for (int q = 0; q < world; ++q) {
         while (ld_acquire_sys(my_flags + q) < s) {
-            if (clock64() - t0 > 4000000000ll) { ok = false; break; }   // ~2 s at 1.9 GHz
+            if (clock64() - t0 > 20000000000ll) { ok = false; break; }  // ~10 s at 1.9 GHz: ranks may be seconds apart at start-up
             __nanosleep(64);
         }
     }

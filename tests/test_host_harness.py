@@ -288,3 +288,41 @@ def test_randomised_states_step_matches_oracle(hh, variant):
         np.testing.assert_allclose(obs, obs_o[i], rtol=2e-7, atol=1e-12)
         seen.add(want)
     assert len(seen) >= (6 if oname == "v2" else 5), seen          # plain, truncated, success(+stopped), crashed, out of bounds ...
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1", "v2m"])
+def test_reset_distributions_and_bounds(hh, variant):
+    """4,000 resets of the device reset code per variant: value ranges and frequencies the reference's reset implies
+    (rl_env_scaledObs.py:40-79 / v1:32-63, utils2/utils.py:12-94)."""
+    ver = {"v2": 2, "v1": 1, "v2m": 3}[variant]
+    n = 4000
+    nw = np.zeros(n, dtype=int)
+    start = np.zeros((n, 3))
+    wps, yaws = [], []
+    for e in range(n):
+        st, obs = hh.reset(ver, 777_000 + e, e % 4)
+        nw[e] = st["n_wp"]
+        start[e] = st["y"][0:3]
+        wps.append(st["wp_list"][: st["n_wp"]])
+        yaws.append(st["final_yaw"])
+        assert st["y"][6] == 1.0 and not np.any(st["y"][3:6]) and not np.any(st["y"][7:13])      # at rest, attitude (0,0,0)
+        assert st["wp_index"] == 0 and st["current_step"] == 0 and st["counter"] == 0 and not st["final_reached"]
+    assert np.all((start[:, :2] >= -1) & (start[:, :2] < 1)) and np.all((start[:, 2] >= 1) & (start[:, 2] < 2))
+    assert abs(start[:, 0].mean()) < 0.05 and abs(start[:, 2].mean() - 1.5) < 0.03
+    allw = np.concatenate(wps)
+    if variant == "v1":
+        assert set(np.unique(nw)) == {1, 2} and abs((nw == 1).mean() - 0.5) < 0.04                 # randint(1, 3)
+        assert np.all((allw[:, :2] >= -1) & (allw[:, :2] < 1)) and np.all((allw[:, 2] >= 1) & (allw[:, 2] < 3))
+    else:
+        if variant == "v2":
+            assert np.all(nw == 1)
+        else:
+            assert set(np.unique(nw)) == {2, 3} and abs((nw == 2).mean() - 0.5) < 0.04             # randint(2, 4)
+        yaws = np.array(yaws)
+        assert np.all((yaws >= -np.pi) & (yaws < np.pi)) and abs(yaws.mean()) < 0.15
+        assert allw[:, 2].min() >= 0.2 - 1e-15                       # curved / helical clamp; linear ends at z >= 0.5
+        assert np.all(np.abs(allw[:, :2]) < 2.9) and allw[:, 2].max() < 4.0 + 1e-9
+        # the LAST waypoint of a linear / curved trajectory is the drawn end point (+ sin(2 pi) ~ -2.4e-16 on one axis), the helix ends
+        # above its start: both keep the end inside the arena
+        last = np.array([w[-1] for w in wps])
+        assert np.all(last[:, 2] >= 0.5 - 1e-9)

@@ -116,3 +116,16 @@ def test_graph_replayed_update_equals_eager_update():
         params[graph] = ppo.net.packed().clone()
         env.close()
     assert float((params[True] - params[False]).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node (run with gpurun --gpus 2)")
+def test_ppo_two_ranks_stay_in_lockstep():
+    """BASELINE configs[4] mechanics on 2 ranks (tools/ppo_multi_rank_check.py under torchrun): sharded envs, VecNormalize statistics
+    through the peer-memory exchange, NCCL gradient all-reduce -> bit-identical parameters and statistics on every rank."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29523", os.path.join(root, "tools", "ppo_multi_rank_check.py")], cwd=root, capture_output=True,
+                       text=True, timeout=400)
+    assert r.returncode == 0 and "PPO_MULTI_RANK_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

@@ -326,3 +326,60 @@ def test_reset_distributions_and_bounds(hh, variant):
         # above its start: both keep the end inside the arena
         last = np.array([w[-1] for w in wps])
         assert np.all(last[:, 2] >= 0.5 - 1e-9)
+
+
+# ------------------------------------------------------------------------------------------------------
+# multi-step drift of the fixed-step throughput modes against the reference's trajectories (same device code, host build);
+# the B200 runs the same checks through the C-ABI in tests/test_gpu_trajectory.py
+# ------------------------------------------------------------------------------------------------------
+def _state_of(b, i):
+    return dict(y=b.y[i].copy(), wp_list=b.wp_list[i].copy(), n_wp=int(b.n_wp[i]), wp_index=int(b.wp_index[i]),
+                last_distance=float(b.last_distance[i]), current_step=int(b.current_step[i]), counter=int(b.counter[i]),
+                final_reached=bool(b.final_reached[i]), final_yaw=float(b.final_yaw[i]))
+
+
+@pytest.mark.parametrize("variant,precision,substeps", [("v2", "f32", 1), ("v2", "f64", 1), ("v1", "f32", 1)])   # the full matrix runs on the GPU
+def test_rk4_trajectory_drift_vs_reference_host(hh, golden_dir, variant, precision, substeps):
+    from drift_bounds import check_step
+    g = load(golden_dir, f"traj_{variant}.npz")
+    n_steps, n_env = g["action"].shape[:2]
+    for i in range(n_env):
+        b = qo.EnvBatch.empty(variant, n_env, max_wp=3)
+        qo.reset_from_uniforms(b, np.arange(n_env), g["uniforms"][:, 0])
+        st, episode, h, last_d = _state_of(b, i), 0, 0, np.nan
+        for t in range(n_steps):
+            cw = st["wp_list"][min(st["wp_index"], st["n_wp"] - 1)]
+            st, obs, rew, flags, ep_len, _ = hh.step(VERS[variant], st, g["action"][t, i], f32=(precision == "f32"), integ="rk4", substeps=substeps)
+            h += 1
+            assert flags == (int(g["terminated"][t, i]) | int(g["truncated"][t, i]) << 1 | (int(g["info"][t, i]) & 0xF) << 2), (i, t)
+            d_ref = np.linalg.norm(g["y"][t, i, :3] - cw)
+            dd = 1.0 if np.isnan(last_d) else last_d - d_ref
+            last_d = d_ref
+            check_step("traj", precision, np.array([float(h)]), st["y"][None], g["y"][t, i][None], np.array([rew]), g["reward"][t, i][None],
+                       np.array([dd]), obs[None], g["terminal_obs"][t, i][None], tag=f"env {i} t={t}")
+            if flags & 3:
+                episode += 1
+                bb = qo.EnvBatch.empty(variant, n_env, max_wp=3)
+                qo.reset_from_uniforms(bb, np.arange(n_env), g["uniforms"][:, episode])
+                st, h, last_d = _state_of(bb, i), 0, np.nan
+
+
+@pytest.mark.parametrize("precision,substeps", [("f32", 1)])
+def test_policy_action_replay_drift_vs_reference_host(hh, golden_dir, precision, substeps):
+    from drift_bounds import check_step
+    g = load(golden_dir, "closed_loop_v2.npz")
+    n = 2
+    b = qo.EnvBatch.empty("v2", n, max_wp=3)
+    qo.reset_from_uniforms(b, np.arange(n), g["uniforms"][:n])
+    for i in range(n):
+        st, last_d = _state_of(b, i), np.nan
+        L = int(g["length"][i])
+        for t in range(L):
+            st, obs, rew, flags, ep_len, _ = hh.step(2, st, g["traj_action"][i, t], f32=(precision == "f32"), integ="rk4", substeps=substeps)
+            d_ref = np.linalg.norm(g["traj_y"][i, t, :3] - g["waypoint"][i])
+            dd = 1.0 if np.isnan(last_d) else last_d - d_ref
+            last_d = d_ref
+            check_step("policy", precision, np.array([t + 1.0]), st["y"][None], g["traj_y"][i, t][None], np.array([rew]),
+                       g["traj_reward"][i, t][None], np.array([dd]), tag=f"ep {i} t={t}")
+            assert bool(flags & 3) == (t == L - 1), (i, t, flags)
+        assert flags == (int(g["terminated"][i]) | int(g["truncated"][i]) << 1 | (int(g["info"][i]) & 0xF) << 2)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 2
+#define QS_ABI_VERSION 3
 
 /* error codes */
 #define QS_OK 0
@@ -52,7 +52,7 @@ extern "C" {
 #define QS_STATE_DIM 13
 #define QS_MAX_WAYPOINTS 3
 #define QS_TRIG_TAB 6
-#define QS_RESET_UNIFORMS 16
+#define QS_RESET_UNIFORMS 18  /* unit uniforms one reset may consume (qs_reset_uniforms) */
 
 typedef struct qs_handle qs_handle;
 
@@ -164,7 +164,6 @@ int qs_get_state(qs_handle* h, const qs_state_view* out, void* stream);
 int qs_set_state(qs_handle* h, const qs_state_view* in, void* stream);
 
 /* The unit uniforms the reset of (global env id, episode) may consume: f64[n,QS_RESET_UNIFORMS]. Test hook. */
-#define QS_RESET_UNIFORMS 18
 int qs_reset_uniforms(qs_handle* h, const int64_t* env_ids, const int32_t* episodes, int64_t n, double* out,
                       void* stream);
 
@@ -218,12 +217,69 @@ const char* qs_vecnorm_last_error(void);
 #define QS_POLICY_FP32 1
 #define QS_POLICY_TENSOR 2
 #define QS_POLICY_TENSOR_FAST 3
+#define QS_POLICY_TENSOR_PIPELINE 4 /* QS_POLICY_TENSOR arithmetic on the warp-specialised pipeline of qs_rollout_step (policy part only) */
+#define QS_POLICY_TENSOR_CHAINS 5   /* QS_POLICY_TENSOR arithmetic on the three-chain kernel (qs_policy_tc.cu) */
+#ifndef QS_POLICY_TENSOR_DEFAULT_PIPELINE
+#define QS_POLICY_TENSOR_DEFAULT_PIPELINE 0 /* which of the two QS_POLICY_TENSOR / AUTO run */
+#endif
 int64_t qs_policy_param_count(int obs_dim);
 int qs_policy_forward(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
                       const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out,
                       float* actions, float* actions_clipped, const float* clip_lo, const float* clip_hi,
                       float* values, float* logp, int impl, void* stream);
 const char* qs_policy_last_error(void);
+
+/* Fused rollout step -----------------------------------------------------------------------------------
+ * ONE kernel launch per rollout step for the whole shard: VecNormalize normalisation of the current observations -> MlpPolicy
+ * forward (actor + critic, tcgen05 split-float16, float32-class accuracy) -> Gaussian sampling, log-prob, clipping to the action
+ * box -> env step (physics, reward, termination, observation) -> auto-reset -> VecNormalize batch moments of the returned
+ * observations (when qs_step_moments is armed; finalised and, with qs_step_moments_merge, merged into the running statistics by
+ * the last CTA of the same launch).
+ * Replaces one iteration of stable_baselines3 OnPolicyAlgorithm.collect_rollouts -- policy(obs) -> np.clip -> VecNormalize /
+ * DummyVecEnv.step_wait -> WaypointQuadEnv.step (call sites initial-implementation-v2/rl_train.py:27-56,
+ * initial-implementation-v1/rl_train_vecN.py:10-36) -- i.e. qs_policy_forward + qs_step (+ the moments kernels) in one launch;
+ * results are identical to that sequence run with the same noise.  float32 / RK4 handles only.
+ *
+ * qs_policy_prepare turns the float32 parameter blob of qs_policy_forward into the operand image the kernel loads (float16 hi/lo
+ * tensor-core operands + the float32 heads, qs_policy_image_bytes() bytes, device, 16-byte aligned); call it once per
+ * parameter update.
+ * sample_mode: QS_SAMPLE_MEAN   deterministic actions (model.predict(deterministic=True), runsim_scaledObs.py:54)
+ *              QS_SAMPLE_NOISE  a = mean + exp(log_std) * noise[n,4]   (caller-supplied standard normal draws)
+ *              QS_SAMPLE_PHILOX the kernel draws the noise itself: Philox4x32-10 keyed on noise_seed, counter = (global env id,
+ *                               *noise_step), Box-Muller; *noise_step (device u64) is incremented once per launch, so a captured
+ *                               CUDA graph replays fresh noise and a batch sharded over ranks draws what the unsharded batch would
+ */
+#define QS_SAMPLE_MEAN 0
+#define QS_SAMPLE_NOISE 1
+#define QS_SAMPLE_PHILOX 2
+typedef struct qs_rollout_args {
+    const void* policy_image;     /* qs_policy_prepare output */
+    const float* obs;             /* f32[n,D] raw observations of the current states (qs_reset / the previous obs_next) */
+    const double* norm_stats;     /* VecNormalize stats f64[1+2D] applied to obs before the policy, or NULL */
+    float norm_eps, norm_clip;
+    int32_t sample_mode;          /* QS_SAMPLE_* */
+    int32_t reserved;
+    const float* noise;           /* f32[n,4], QS_SAMPLE_NOISE */
+    uint64_t noise_seed;          /* QS_SAMPLE_PHILOX */
+    uint64_t* noise_step;         /* QS_SAMPLE_PHILOX: device counter word */
+    float clip_lo[4], clip_hi[4]; /* action box (SB3 clips before env.step) */
+    float* obs_norm_out;          /* f32[n,D] or NULL: the normalised observations the policy saw (RolloutBuffer.observations) */
+    float* actions_out;           /* f32[n,4] sampled, unclipped (RolloutBuffer.actions) */
+    float* actions_clipped_out;   /* f32[n,4] or NULL: what the envs were stepped with */
+    float* values_out;            /* f32[n] */
+    float* logp_out;              /* f32[n] */
+    float* obs_next;              /* f32[n,D] observations after the step (reset obs where done); may alias obs */
+    float* reward_out;            /* f32[n] */
+    uint8_t* flags_out;           /* u8[n] QS_FLAG_* */
+    float* terminal_obs_out;      /* f32[n,D] or NULL, rows of done envs */
+    float* ep_return_out;         /* f32[n] or NULL, rows of done envs */
+    int32_t* ep_len_out;          /* i32[n] or NULL, rows of done envs */
+} qs_rollout_args;
+int64_t qs_policy_image_bytes(void);
+int qs_policy_prepare(const float* params, int obs_dim, void* image_out, void* stream);
+int qs_rollout_step(qs_handle* h, const qs_rollout_args* a, void* stream);
+/* 0, or the code of the internal hand-over that timed out (every in-kernel wait is bounded; synchronises the device, clears) */
+int qs_rollout_status(void);
 
 /* Generalized advantage estimation ------------------------------------------------------------------
  * Replaces stable_baselines3 RolloutBuffer.compute_returns_and_advantage (inside model.learn(), reference call sites

@@ -16,7 +16,7 @@ from .quad_constants import QUAD
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QS_LIB_PATH") or os.path.join(HERE, "lib", "libquadsim.so")
 
-QS_ABI_VERSION = 2
+QS_ABI_VERSION = 3
 QS_F32, QS_F64 = 0, 1
 QS_RK4, QS_LSODA = 0, 1
 FLAG_TERMINATED, FLAG_TRUNCATED, FLAG_SUCCESS, FLAG_STOPPED = 0x01, 0x02, 0x04, 0x08
@@ -83,6 +83,20 @@ def make_config(env_version=2, n_envs=1, precision="f32", integrator="rk4", subs
     return c
 
 
+class QsRolloutArgs(C.Structure):
+    """qs_rollout_args of include/quadsim.h."""
+    _fields_ = [("policy_image", C.c_void_p), ("obs", C.c_void_p), ("norm_stats", C.c_void_p),
+                ("norm_eps", C.c_float), ("norm_clip", C.c_float), ("sample_mode", C.c_int32), ("reserved", C.c_int32),
+                ("noise", C.c_void_p), ("noise_seed", C.c_uint64), ("noise_step", C.c_void_p),
+                ("clip_lo", C.c_float * 4), ("clip_hi", C.c_float * 4),
+                ("obs_norm_out", C.c_void_p), ("actions_out", C.c_void_p), ("actions_clipped_out", C.c_void_p),
+                ("values_out", C.c_void_p), ("logp_out", C.c_void_p), ("obs_next", C.c_void_p), ("reward_out", C.c_void_p),
+                ("flags_out", C.c_void_p), ("terminal_obs_out", C.c_void_p), ("ep_return_out", C.c_void_p), ("ep_len_out", C.c_void_p)]
+
+
+SAMPLE_MEAN, SAMPLE_NOISE, SAMPLE_PHILOX = 0, 1, 2
+
+
 class QsPidGains(C.Structure):
     """qs_pid_gains of include/quadsim.h (order x, y, z, phi, theta, psi)."""
     _fields_ = [("kp", C.c_double * 6), ("kd", C.c_double * 6), ("ki", C.c_double * 6), ("max_integral", C.c_double)]
@@ -122,6 +136,12 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.qs_set_state.argtypes = [vp, C.POINTER(QsStateView), vp]
     lib.qs_reset_uniforms.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.qs_lsoda_stats.argtypes = [vp, vp, vp, vp]
+    lib.qs_policy_image_bytes.restype = i64
+    lib.qs_policy_prepare.argtypes = [vp, i32, vp, vp]
+    lib.qs_policy_prepare.restype = C.c_int
+    lib.qs_rollout_step.argtypes = [vp, C.POINTER(QsRolloutArgs), vp]
+    lib.qs_rollout_step.restype = C.c_int
+    lib.qs_rollout_status.restype = C.c_int
     lib.qs_pid_default_gains.argtypes = [C.POINTER(QsPidGains)]
     lib.qs_pid_default_gains.restype = None
     lib.qs_pid_run.argtypes = [vp, C.POINTER(QsPidGains), C.c_double] + [vp] * 8 + [i32, vp]

@@ -175,6 +175,7 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     h->mom_merge = nullptr;
     h->range_first = 0;
     h->range_count = 0;
+    h->ro_ticket = nullptr;
     h->ls_tables = nullptr;
     h->ls_counters = nullptr;
     h->ls_steps = nullptr;
@@ -200,6 +201,7 @@ int qs_destroy(qs_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->pool) cudaFree(h->pool);
     if (h->mom_scratch) cudaFree(h->mom_scratch);
+    if (h->ro_ticket) cudaFree(h->ro_ticket);
     if (h->ls_tables) cudaFree(h->ls_tables);
     if (h->ls_counters) cudaFree(h->ls_counters);
     if (h->ls_steps) cudaFree(h->ls_steps);

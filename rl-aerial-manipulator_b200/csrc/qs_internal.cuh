@@ -16,6 +16,7 @@ struct qs_handle {
     qs::LsodaTables* ls_tables;
     int32_t* ls_counters;
     double* ls_steps;
+    unsigned int* ro_ticket;  // qs_rollout_step: last-CTA election counter
     int64_t range_first, range_count;   // qs_step_range: the sub-range the next launch covers (count 0 = all envs)
     int num_sms;
     bool initialized;

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace qs {
 
@@ -230,6 +231,10 @@ int launch_policy_tc(int precise, const float* params, int obs_dim, const float*
                      const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out, float* actions,
                      float* actions_clipped, const float* clip_lo, const float* clip_hi, float* values, float* logp,
                      cudaStream_t stream, const char** err_out);
+int launch_policy_pipeline(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n, const double* norm_stats,
+                           float norm_eps, float norm_clip, float* obs_norm_out, float* actions, float* actions_clipped,
+                           const float* clip_lo, const float* clip_hi, float* values, float* logp, cudaStream_t stream,
+                           const char** err_out);
 
 }  // namespace qs
 
@@ -250,14 +255,23 @@ int qs_policy_forward(const float* params, int obs_dim, const float* obs, const 
         return QS_EINVAL;
     }
     if (n == 0) return QS_OK;
-    if (impl < 0 || impl > 3) {
-        snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward: impl must be QS_POLICY_AUTO, _FP32, _TENSOR or _TENSOR_FAST");
+    if (impl < 0 || impl > 5) {
+        snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward: impl must be one of QS_POLICY_*");
         return QS_EINVAL;
     }
     // QS_POLICY_AUTO: the tcgen05 kernel (float32-accurate split-float16 mode) wins once there are enough 128-env tiles
     // to fill the SMs (profiles/r01/policy_paths.md); below that the FFMA kernel's finer 64-env tiles do
-    if (impl == QS_POLICY_TENSOR || impl == QS_POLICY_TENSOR_FAST || (impl == QS_POLICY_AUTO && n >= 16384)) {
+    if (impl >= QS_POLICY_TENSOR || (impl == QS_POLICY_AUTO && n >= 16384)) {
         const char* msg = nullptr;
+        // float32-accurate tensor mode: the warp-specialised pipeline (qs_rollout.cu) or the chain kernels (qs_policy_tc.cu); both
+        // stay selectable (QS_POLICY_TENSOR_PIPELINE / _CHAINS) for A/B measurements, QS_POLICY_TENSOR and AUTO take the default
+        const bool pipeline = impl == QS_POLICY_TENSOR_PIPELINE || ((impl == QS_POLICY_TENSOR || impl == QS_POLICY_AUTO) && QS_POLICY_TENSOR_DEFAULT_PIPELINE);
+        if (pipeline) {
+            const int rc = launch_policy_pipeline(params, obs_dim, obs, noise, n, norm_stats, norm_eps, norm_clip, obs_norm_out, actions,
+                                                  actions_clipped, clip_lo, clip_hi, values, logp, (cudaStream_t)stream, &msg);
+            if (rc != QS_OK && msg) snprintf(g_policy_error, sizeof(g_policy_error), "%s", msg);
+            return rc;
+        }
         const int rc = launch_policy_tc(impl != QS_POLICY_TENSOR_FAST, params, obs_dim, obs, noise, n, norm_stats, norm_eps, norm_clip,
                                         obs_norm_out, actions, actions_clipped, clip_lo, clip_hi, values, logp, (cudaStream_t)stream, &msg);
         if (rc != QS_OK && msg) snprintf(g_policy_error, sizeof(g_policy_error), "%s", msg);

@@ -57,7 +57,7 @@ def pack_params(sd: dict, obs_dim: int) -> np.ndarray:
     return np.concatenate(parts).astype(np.float32)
 
 
-IMPL = {"auto": 0, "fp32": 1, "tensor": 2, "tensor_fast": 3}
+IMPL = {"auto": 0, "fp32": 1, "tensor": 2, "tensor_fast": 3, "tensor_pipeline": 4, "tensor_chains": 5}
 
 
 class MlpPolicyKernel:

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 18, names
     for n in names:
         assert hasattr(lib, n), f"libquadsim.so does not export {n}"
-    assert lib.qs_abi_version() == 2
+    assert lib.qs_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure path")

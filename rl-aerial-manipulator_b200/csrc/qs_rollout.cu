@@ -36,8 +36,18 @@ namespace ro {
 using namespace tc;
 
 constexpr int EPI_WARPS = 8, ENV_WARPS = 4, MMA_WARPS = 2;
-constexpr int W_ENV0 = EPI_WARPS, W_MMA0 = EPI_WARPS + ENV_WARPS;
-constexpr int RO_THREADS = 32 * (EPI_WARPS + ENV_WARPS + MMA_WARPS);     // 448
+// A/B switch (QS_RO_ENV_FIRST): which role gets the low warp ids -- the schedulers favour older (lower) warps when several are
+// ready, and the env warps' few MUFU ops queue behind the epilogue warps' thousands
+#ifndef QS_RO_ENV_FIRST
+#define QS_RO_ENV_FIRST 0
+#endif
+#ifndef QS_RO_LDBUF
+#define QS_RO_LDBUF 1
+#endif
+constexpr int W_EPI0 = QS_RO_ENV_FIRST ? ENV_WARPS : 0, W_ENV0 = QS_RO_ENV_FIRST ? 0 : EPI_WARPS, W_MMA0 = EPI_WARPS + ENV_WARPS;
+// 14 working warps; the block is padded to 16 because registers are allocated per 4 warps: 448 threads cannot have more than the
+// 128 registers 512 threads get (a 448 x 144 launch is refused)
+constexpr int RO_THREADS = 512;
 constexpr int XBUFS = 3;
 constexpr uint32_t SLOT_COLS = 256, C_D1 = 0, C_D2 = 128, C_D3 = 192;
 
@@ -94,23 +104,54 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded parity wait (all lanes poll).  false = gave up: the caller leaves its role, the status word says where.
-__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, int code) {
+// A plain try_wait loop returns every ~30 cycles; with ten warps of an SM waiting most of the time the polling alone was 40 % of
+// all issued instructions (ncu, profiles/r02) and starved the warps that had work.  So: the suspend-time hint of try_wait (the
+// thread sleeps in the barrier unit until the phase completes or the hint expires) and a nanosleep between polls.
+#ifndef QS_RO_WAIT_HINT_NS
+#define QS_RO_WAIT_HINT_NS 4000
+#endif
+#ifndef QS_RO_BACKOFF_NS
+#define QS_RO_BACKOFF_NS 32
+#endif
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+#if QS_RO_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)QS_RO_WAIT_HINT_NS)
+        : "memory");
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+#endif
+    return ok;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int code) {
     for (uint32_t it = 0; it < (1u << 22); ++it) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return true;
+#if QS_RO_BACKOFF_NS > 0
+        __nanosleep(QS_RO_BACKOFF_NS);
+#endif
+        if (mbar_try(bar, parity)) return true;
         if ((it & 0xFFFF) == 0xFFFF && *reinterpret_cast<volatile int*>(&g_ro_status) != 0) break;   // somebody else already gave up
     }
     atomicCAS(&g_ro_status, 0, code);
     return false;
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, int code) {
+    if (mbar_try(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, code);
 }
 // D[tmem] (+)= A[smem] . B[smem]^T
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -270,28 +311,10 @@ __device__ __forceinline__ void role_mma(const Ctx& c, int slot) {
 // ---------------------------------------------------------------------------------------------------------------------
 // Epilogue warp (slot, quadrant): 32 env rows = its TMEM lanes.
 // ---------------------------------------------------------------------------------------------------------------------
-// NCH accumulator chunks at tm + col0 -> tanh -> hi | lo in place; chunk ch signalled on bars[ch] as soon as it is stored.
-// The TMEM load of chunk ch + 1 is in flight while chunk ch is computed.
-template <int NCH>
-__device__ __forceinline__ void epilogue_chunks(const Ctx& c, uint32_t tm, int bar0, int lane) {
-    uint32_t va[32], vb[32];
-    float y[32];
-    tmem_ld32(tm, va);
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-        uint32_t* cur = (ch & 1) ? vb : va;
-        uint32_t* nxt = (ch & 1) ? va : vb;
-        tmem_ld_wait32(cur);
-        if (ch + 1 < NCH) tmem_ld32(tm + 32u * (ch + 1), nxt);
-        tanh32<true>(cur, y);
-        put32_rn(tm + 32u * ch, y);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(c.bar(bar0 + ch));
-    }
-}
-
+// The hot loops are ROLLED on purpose: B200's instruction caches are small (L0 ~6 KB per scheduler, L1.5 32 KB per SM) and four
+// different instruction streams share them here.  With the epilogues unrolled per chunk the kernel's hot code was ~100 KB and
+// `no_inst` (instruction fetch) was the top stall of every role (ncu, profiles/r02); one ~5 KB chunk routine serves all
+// six hidden-layer chunks, another the two head chunks.
 __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int quad, int lane, const float* sC, float4* s_mean, float* s_val) {
     const uint32_t tm = c.tmem + slot * SLOT_COLS + ((uint32_t)(quad * 32) << 16);
     const int role = 100 + slot * 50;
@@ -303,38 +326,46 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int quad, 
 #pragma unroll 1
         for (int net = 0; net < 2; ++net, ++job) {
             const uint32_t par = job & 1u;
-            if (!mbar_wait_bounded(c.bar(B_D1 + slot), par, role + B_D1 + 1)) return;
-            tc_fence_after();
-            epilogue_chunks<4>(c, tm + C_D1, B_H1 + slot * 4, lane);
-            if (!mbar_wait_bounded(c.bar(B_D2 + slot), par, role + B_D2 + 1)) return;
-            tc_fence_after();
-            epilogue_chunks<2>(c, tm + C_D2, B_H2 + slot * 2, lane);
+            // chunks 0-3: layer-1 accumulator D1 -> H1; chunks 4-5: layer-2 accumulator D2 -> H2 (D2 follows D1 in the slot's columns).
+            // Each: tcgen05.ld -> tanh -> hi | lo split in place -> signal the MMA warp.
+#pragma unroll 1
+            for (int ch = 0; ch < 6; ++ch) {
+                if (ch == 0 && !mbar_wait_bounded(c.bar(B_D1 + slot), par, role + B_D1 + 1)) return;
+                if (ch == 4 && !mbar_wait_bounded(c.bar(B_D2 + slot), par, role + B_D2 + 1)) return;
+                if (ch == 0 || ch == 4) tc_fence_after();
+                uint32_t v[32];
+                float y[32];
+                const uint32_t col = tm + 32u * (uint32_t)ch;
+                tmem_ld32(col, v);
+                tmem_ld_wait32(v);
+                tanh32<true>(v, y);
+                put32_rn(col, y);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.bar(ch < 4 ? B_H1 + slot * 4 + ch : B_H2 + slot * 2 + (ch - 4)));
+            }
             if (!mbar_wait_bounded(c.bar(B_D3 + slot), par, role + B_D3 + 1)) return;
             tc_fence_after();
             float o[NACT];
 #pragma unroll
             for (int j = 0; j < NACT; ++j) o[j] = sC[C_BH + net * NACT + j];
-            {
-                uint32_t va[32], vb[32];
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t v[32];
                 float y[32];
-                tmem_ld32(tm + C_D3, va);
-                tmem_ld32(tm + C_D3 + 32, vb);
-                tmem_ld_wait32(va);
-                tmem_ld_wait32(vb);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(c.bar(B_D3FREE + slot));      // layer 3 of the next job may overwrite D3
-                const float4* wh = reinterpret_cast<const float4*>(sC + C_WH + net * N3 * NACT);
-                tanh32<true>(va, y);
+                tmem_ld32(tm + C_D3 + 32u * (uint32_t)ch, v);
+                tmem_ld_wait32(v);
+                if (ch == 1) {                                           // layer 3 of the next job may overwrite D3
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(c.bar(B_D3FREE + slot));
+                }
+                tanh32<true>(v, y);
+                const float4* wh = reinterpret_cast<const float4*>(sC + C_WH + net * N3 * NACT) + 32 * ch;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const float4 w = wh[q];
-                    o[0] = fmaf(y[q], w.x, o[0]); o[1] = fmaf(y[q], w.y, o[1]); o[2] = fmaf(y[q], w.z, o[2]); o[3] = fmaf(y[q], w.w, o[3]);
-                }
-                tanh32<true>(vb, y);
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float4 w = wh[32 + q];
                     o[0] = fmaf(y[q], w.x, o[0]); o[1] = fmaf(y[q], w.y, o[1]); o[2] = fmaf(y[q], w.z, o[2]); o[3] = fmaf(y[q], w.w, o[3]);
                 }
             }
@@ -459,21 +490,21 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int qu
     const float sd[4] = {__expf(ls[0]), __expf(ls[1]), __expf(ls[2]), __expf(ls[3])};
     const float lp0 = -(ls[0] + ls[1] + ls[2] + ls[3]) - 4.0f * 0.9189385332046727f;
 
-    for (int i = 0; i < 2 && i < c.cnt; ++i)
-        if (!stage_x<OBS>(c, p, i, quad, lane, smem, s_norm)) return;
     EnvState<float, VER> s_nx;
     if (FUSED) {
         const int64_t e0 = ((int64_t)blockIdx.x) * ROWS + row;
         if (e0 < p.n) pool_load<float, VER>(sp.pool, sp.n, e0, s_nx);
     }
-    for (int i = 0; i < c.cnt; ++i) {
+#pragma unroll 1
+    for (int i = -2; i < c.cnt; ++i) {                   // iterations -2, -1 only stage the first two X tiles (one call site: code size)
+        if (i + 2 < c.cnt && !stage_x<OBS>(c, p, i + 2, quad, lane, smem, s_norm)) return;
+        if (i < 0) continue;
         const int slot = i & 1;
         const uint32_t k = (uint32_t)i >> 1;
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
         const int64_t e0 = tile * ROWS + quad * 32;
         const int64_t e = e0 + lane;
         const bool live = e < p.n;
-        if (i + 2 < c.cnt && !stage_x<OBS>(c, p, i + 2, quad, lane, smem, s_norm)) return;
         EnvState<float, VER> s;
         if (FUSED) {
             s = s_nx;
@@ -506,7 +537,7 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int qu
                 float Fcmd, Mcmd[3], F, M[3];
                 scale_action<float>(sp.model, act, sp.scale_f32, Fcmd, Mcmd);
                 mix_and_clamp<float>(sp.model, Fcmd, Mcmd, F, M);
-                rk4_step<float>(sp.model, s.y, F, M, sp.substeps);
+                rk4_step_rolled<float>(sp.model, s.y, F, M, sp.substeps);
                 renormalise_quat<float>(s.y);
                 float reward;
                 int ep_len;
@@ -566,7 +597,7 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int qu
 // The kernel.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int VER, bool FUSED>
-__global__ void __maxnreg__(144) rollout_kernel(const RoParams p) {
+__global__ void __launch_bounds__(RO_THREADS, 1) rollout_kernel(const RoParams p) {
     constexpr int OBS = EnvTraits<VER>::OBS;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -634,9 +665,9 @@ __global__ void __maxnreg__(144) rollout_kernel(const RoParams p) {
     const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
     c.cnt = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-    if (warp < W_ENV0) role_epilogue(c, warp >> 2, warp & 3, lane, sC, s_mean, s_val);
-    else if (warp < W_MMA0) role_env<VER, FUSED>(c, p, warp & 3, lane, smem, sC, s_mean, s_val, noise_step);
-    else role_mma(c, warp - W_MMA0);
+    if (warp >= W_EPI0 && warp < W_EPI0 + EPI_WARPS) role_epilogue(c, (warp - W_EPI0) >> 2, warp & 3, lane, sC, s_mean, s_val);
+    else if (warp >= W_ENV0 && warp < W_ENV0 + ENV_WARPS) role_env<VER, FUSED>(c, p, warp & 3, lane, smem, sC, s_mean, s_val, noise_step);
+    else if (warp < W_MMA0 + MMA_WARPS) role_mma(c, warp - W_MMA0);
 
     tc_fence_before();
     __syncthreads();

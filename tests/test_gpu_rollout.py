@@ -93,6 +93,11 @@ def test_fused_rollout_step_equals_separate_calls(golden_dir, n, env_version):
     env_a, pol = make(n, golden_dir, seed=11, env_version=env_version)
     env_b, _ = make(n, golden_dir, seed=11, env_version=env_version)
     d = env_a.obs_dim
+    y = env_a.get_state(["y"])["y"]
+    y[: n // 3, 2] = 0.13                          # a third of the envs start just above the crash height: terminations + auto-resets
+    y[: n // 3, 5] = -0.5
+    env_a.set_state(y=y)
+    env_b.set_state(y=y)
     rms_a, rms_b = DeviceRunningMeanStd(d, "cuda"), DeviceRunningMeanStd(d, "cuda")
     for rms, env in ((rms_a, env_a), (rms_b, env_b)):
         rms.update(env.obs)
@@ -103,8 +108,6 @@ def test_fused_rollout_step_equals_separate_calls(golden_dir, n, env_version):
     n_done = 0
     for t in range(40):
         noise = torch.randn((n, 4), device="cuda", generator=g)
-        if t % 4 == 0:
-            noise[: n // 3, 0] -= 6.0          # a third of the envs cut thrust now and then: crashes and auto-resets
         # separate calls on env_b
         a_b, v_b, lp_b = pol.forward(env_b.obs, noise, norm_stats=rms_b.stats, obs_norm_out=obs_norm_b)
         a_b, v_b, lp_b, ac_b = a_b.clone(), v_b.clone(), lp_b.clone(), pol.actions_clipped.clone()
@@ -240,7 +243,7 @@ def test_fused_rollout_1M_envs_properties(golden_dir):
     m = t2n(rms._moments)
     x = env.obs.double()
     assert m[0] == n
-    np.testing.assert_allclose(m[1:21], t2n(x.mean(0)), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(m[1:21], t2n(x.mean(0)), rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(m[21:], t2n(x.var(0, unbiased=False)) * n, rtol=1e-7, atol=1e-9)
     assert abs(float(rms.count) - (1e-4 + 31 * n)) < 1.0
     env.close()

@@ -14,7 +14,7 @@ from rl_aerial_manipulator_b200.rollout import FusedRollout  # noqa: E402
 from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 NPZ = os.path.join(ROOT, "tests", "golden", "policy_v2.npz")
 
 

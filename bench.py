@@ -50,46 +50,75 @@ POLICY_FLOPS = 60032                                                         # a
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference step on the host cores
+# CPU arm: the reference's own step on the host cores (oracle/_ref, staged by oracle/make_ref.py), else the oracle port
 # --------------------------------------------------------------------------------------------------
 _CPU = {}
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-def _cpu_init(n_env):
-    """Pool initializer: one v2 VecOracle per worker process (float64, SciPy LSODA like quadcopter.py:113, auto-reset)."""
+def reference_staged() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "MANIFEST.json"))
+
+
+def _cpu_init(n_env, kind):
+    """Pool initializer, one per worker process.
+    kind "reference": n_env UNMODIFIED `WaypointQuadEnv` objects (initial-implementation-v2/rl_env_scaledObs.py:9) under the
+    gymnasium stub, stepped one after the other with reset-on-done -- SB3's DummyVecEnv.step_wait loop; the env's print()s
+    go to /dev/null.
+    kind "port": one v2 VecOracle (oracle/quad_oracle.py: float64, the same SciPy LSODA call as quadcopter.py:113, auto-reset)."""
     os.environ["OMP_NUM_THREADS"] = "1"
     import numpy as np
 
-    from oracle import quad_oracle as qo
-
     rng = np.random.default_rng(os.getpid())
-    vec = qo.VecOracle("v2", n_env, lambda ids, eps: rng.random((len(ids), qo.N_UNIFORMS)), integrator="lsoda")
-    vec.reset()
-    _CPU.update(np=np, rng=rng, vec=vec, n=n_env, lo=np.array([0, -1, -1, -1.0]), hi=np.array([2, 1, 1, 1.0]))
+    _CPU.update(np=np, rng=rng, n=n_env, kind=kind, lo=np.array([0, -1, -1, -1.0]), hi=np.array([2, 1, 1, 1.0]))
+    if kind == "reference":
+        os.environ["QS_REFERENCE_ROOT"] = REF_DIR
+        os.dup2(os.open(os.devnull, os.O_WRONLY), 1)
+        sys.stdout = open(os.devnull, "w")
+        from oracle import ref_harness
+
+        np.random.seed(os.getpid() & 0x7FFFFFFF)
+        envs = [ref_harness.make_env("v2") for _ in range(n_env)]
+        for e in envs:
+            e.reset()
+        _CPU.update(envs=envs)
+    else:
+        from oracle import quad_oracle as qo
+
+        vec = qo.VecOracle("v2", n_env, lambda ids, eps: rng.random((len(ids), qo.N_UNIFORMS)), integrator="lsoda")
+        vec.reset()
+        _CPU.update(vec=vec)
 
 
 def _cpu_chunk(seconds):
     """Step this worker's envs with uniform-random float32 actions for `seconds`; returns (env-steps, elapsed)."""
-    np, rng, vec, n = _CPU["np"], _CPU["rng"], _CPU["vec"], _CPU["n"]
+    np, rng, n = _CPU["np"], _CPU["rng"], _CPU["n"]
     done, t0 = 0, time.perf_counter()
     while True:
         a = (_CPU["lo"] + (_CPU["hi"] - _CPU["lo"]) * rng.random((n, 4))).astype(np.float32)
         with np.errstate(all="ignore"):
-            vec.step(a)
+            if _CPU["kind"] == "reference":
+                for e, act in zip(_CPU["envs"], a):
+                    _, _, terminated, truncated, _ = e.step(act)
+                    if terminated or truncated:
+                        e.reset()
+            else:
+                _CPU["vec"].step(a)
         done += n
         if time.perf_counter() - t0 >= seconds:
             return done, time.perf_counter() - t0
 
 
 class CpuArm:
-    """The CPU arm: oracle port of the reference step, one process per host core (the SubprocVecEnv-style layout)."""
+    """The CPU arm, one process per host core (the SubprocVecEnv-style layout)."""
 
-    def __init__(self, n_env: int = 8, procs: int | None = None):
+    def __init__(self, n_env: int = 8, procs: int | None = None, kind: str | None = None):
         import multiprocessing as mp
 
         self.cores = procs or (os.cpu_count() or 1)
         self.n_env = n_env
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(n_env,))
+        self.kind = kind or ("reference" if reference_staged() else "port")
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(n_env, self.kind))
 
     def sample(self, seconds: float):
         t0 = time.perf_counter()
@@ -102,16 +131,26 @@ class CpuArm:
         self.pool.join()
 
     def describe(self, total, wall, what):
-        return (f"{total} env-steps of v2 (float64, scipy LSODA like quadcopter.py:113, auto-reset, uniform-random float32 actions) by "
-                f"oracle/quad_oracle.py, {self.cores} processes x {self.n_env} envs, {what} (wall {wall:.1f} s)")
+        who = ("the UNMODIFIED reference WaypointQuadEnv.step + reset-on-done (oracle/_ref, staged by oracle/make_ref.py; gymnasium stub)"
+               if self.kind == "reference" else "oracle/quad_oracle.py (NumPy port; same SciPy LSODA call as quadcopter.py:113)")
+        return (f"{total} env-steps of v2 (float64, scipy odeint/LSODA, auto-reset, uniform-random float32 actions) by {who}, "
+                f"{self.cores} processes x {self.n_env} envs, {what} (wall {wall:.1f} s)")
 
 
 def cpu_baseline(seconds: float = 12.0) -> dict:
-    arm = CpuArm()
-    arm.sample(0.5)
-    total, wall = arm.sample(seconds)
-    arm.close()
-    return {"value": total / wall, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.describe(total, wall, f"one {seconds:.0f} s sample")}
+    """Reference step on all host cores (kind "reference" when oracle/_ref is staged), the port's number beside it."""
+    out = None
+    for kind, secs in ((("reference", seconds), ("port", 4.0)) if reference_staged() else (("port", seconds),)):
+        arm = CpuArm(kind=kind)
+        arm.sample(0.5)
+        total, wall = arm.sample(secs)
+        arm.close()
+        rec = {"value": total / wall, "unit": UNIT, "cores": arm.cores, "kind": kind, "sample": arm.describe(total, wall, f"one {secs:.0f} s sample")}
+        if out is None:
+            out = rec
+        else:
+            out["port"] = rec
+    return out
 
 
 def run_reference_arm(args) -> None:
@@ -129,13 +168,14 @@ def run_reference_arm(args) -> None:
     wall = time.perf_counter() - t0
     arm.close()
     value = total / wall
-    base = {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
+    base = {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
             "sample": arm.describe(total, wall, f"{args.steps} samples of {per_step * 1e3:.0f} ms")}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "note": "CPU oracle port of the reference step (the reference tree is not on the GPU box); "
-                       "each step = one bounded sample on all host cores"},
+            "config": {"workload": workload_name(args), "envs_per_process": arm.n_env, "integrator": "scipy odeint (LSODA)",
+                       "note": ("the unmodified reference env stepped on all host cores" if arm.kind == "reference" else
+                                "CPU oracle port of the reference step (oracle/_ref not staged)") + "; each step = one bounded sample on all host cores"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -198,15 +238,16 @@ def measured_peak(key: str, fallback: float) -> tuple[float, str]:
     return fallback, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel_key: str):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/roofline_traffic.json)."""
+def ncu_traffic_table() -> dict:
+    """kernel name -> dram bytes (read + write) per launch at 1,048,576 envs, from the committed `ncu --set full` captures of
+    exactly these kernels (profiles/roofline_traffic.json names the .csv each number comes from)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel_key)
+            return {k: v for k, v in json.load(open(p)).items() if isinstance(v, (int, float))}
         except Exception:  # noqa: BLE001
-            return None
-    return None
+            return {}
+    return {}
 
 
 def workload_name(args) -> str:
@@ -218,6 +259,72 @@ def workload_name(args) -> str:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def graph_time(fn, steps, unroll, dev, barrier=None):
+    """ms per call of `fn`, replayed from a CUDA graph of `unroll` calls (CUDA events on the replay stream, warm replay first)."""
+    import torch
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for i in range(unroll):
+            fn(i)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(unroll):
+            fn(i)
+    g.replay()
+    (barrier or (lambda: torch.cuda.synchronize(dev)))()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, steps // unroll)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    (barrier or (lambda: torch.cuda.synchronize(dev)))()
+    return e0.elapsed_time(e1) / (reps * unroll), g
+
+
+def step_extra(n, precision, integrator, dev, seed, steps):
+    """One extra workload line: the bare env step (configs[2]) on `n` envs, actions regenerated on the device every step."""
+    import torch
+
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    env = BatchedQuadEnv(n, env_version=2, precision=precision, integrator=integrator, device=dev.index, seed=seed)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lo = torch.tensor([0.0, -1, -1, -1], device=dev)
+    span = torch.tensor([2.0, 2, 2, 2], device=dev)
+    u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
+    many = integrator == "rk4" and hasattr(env, "step_many")
+    T = 16
+    if many:
+        # T steps per launch, state in registers, uniform actions drawn in the kernel (Philox on (seed, global env id, step))
+        ms, graph = graph_time(lambda i: env.step_many(T), steps, 1, dev)
+        ms /= T
+        launches, actions = 1.0 / T, f"in-kernel Philox uniform over the action box, {T} steps per launch (qs_step_many)"
+    else:
+        def one(i):
+            u.uniform_(generator=g)
+            torch.addcmul(lo, u, span, out=a)
+            env.step(a)
+        ms, graph = graph_time(one, steps, 4 if integrator == "rk4" else 1, dev)
+        launches, actions = 1, "uniform over the action box, regenerated on the device every step (2 torch kernels inside the timed region)"
+    del graph
+    env.close()
+    algo = ALGO_BYTES[("v2", precision)]
+    peak, peak_src = measured_peak("hbm_gbs", 6650.0)
+    ach = algo * n / (ms / 1e3) / 1e9
+    tag = f"{n // (1 << 20)}M" if n % (1 << 20) == 0 else str(n)
+    return {"workload": f"v2_step_{tag}_{precision}" + ("_lsoda" if integrator == "lsoda" else ""), "value": n / (ms / 1e3), "unit": UNIT,
+            "ms_per_step": ms, "dtype": precision, "integrator": integrator, "actions": actions, "our_launches_per_step": launches,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": algo,
+                         "note": ("parity mode: adaptive LSODA, ~35 divergent f-evals per step -- latency-bound, not a throughput mode" if integrator == "lsoda" else
+                                  ("working set fits the 126 MB L2" if n * 185 < 126e6 else "working set exceeds L2"))}}
+
+
 def run_gpu(args) -> None:
     import numpy as np
     import torch
@@ -240,42 +347,48 @@ def run_gpu(args) -> None:
     env = BatchedQuadEnv(n, env_version=2, precision=args.precision, integrator="rk4", substeps=args.substeps,
                          device=local, env_id_offset=rank * n, seed=args.seed)
     env.reset()
-    launches_per_step = 1
-    policy = None
-    vn = None
+    policy = vn = fused = None
+    g = torch.Generator(device=dev).manual_seed(args.seed + rank)
+    lo = torch.tensor([0.0, -1, -1, -1], device=dev)
+    span = torch.tensor([2.0, 2, 2, 2], device=dev)
+    parts = {}                          # name -> callable(i): the launches of one step, by kernel, for the per-kernel timing
     if args.workload == "rollout":
         from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
         from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd
         policy = MlpPolicyKernel.from_npz(os.path.join(ROOT, "tests", "golden", "policy_v2.npz"), device=dev)
-        launches_per_step = 2
         if args.vecnorm:
-            # VecNormalize(norm_obs=True): moments of this rank's shard -> (N>1) all-gather of 2D+1 doubles fused with the Chan
-            # merge in one kernel over NVLink peer memory (qs_xchg_merge; NCCL all-gather + merge kernel if peers cannot be
-            # mapped) -> normalisation fused into the policy kernel's obs load
+            # VecNormalize(norm_obs=True): the step reduces the moments of the obs it returns; on one GPU the kernel that finishes
+            # them also merges them into the running statistics, with several ranks one kernel does the all-gather (2D+1 doubles
+            # per rank over NVLink peer memory) and the Chan merge (qs_xchg_merge; NCCL all-gather + merge kernel as fallback)
             vn = DeviceRunningMeanStd(env.obs_dim, dev, exchange=args.vecnorm_exchange)
-            # the step kernel reduces the obs it returns (no separate read pass); on one GPU the kernel that finishes the
-            # moments also merges them into the running statistics, with several ranks the exchange kernel does
             vn.attach(env, merge=(world == 1))
-            launches_per_step = 3 if world == 1 else 4       # env step + moments_final(+merge) [+ exchange/merge] + policy forward
-    # uniform-random actions over the action box, pre-generated ring (step workload) / sampling noise (rollout)
-    g = torch.Generator(device=dev).manual_seed(args.seed + rank)
-    lo = torch.tensor([0.0, -1, -1, -1], device=dev)
-    hi = torch.tensor([2.0, 1, 1, 1], device=dev)
-    ring = [(lo + (hi - lo) * torch.rand((n, 4), device=dev, generator=g)).contiguous() for _ in range(4)]
-    noise = [torch.randn((n, 4), device=dev, generator=g) for _ in range(4)] if policy else None
-    act_lo, act_hi = lo, hi
+        if args.rollout == "fused":
+            from rl_aerial_manipulator_b200.rollout import FusedRollout
+            # ONE kernel per step: normalise -> tcgen05 policy forward -> in-kernel Philox Gaussian sampling -> clip -> env step ->
+            # auto-reset -> moments (+ merge on one GPU)
+            fused = FusedRollout(env, policy, vecnorm=vn, sample="philox", noise_seed=args.seed)
+            parts["rollout_kernel<v2,fused>"] = lambda i: fused.step()
+            if vn is not None and world > 1:
+                parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
+        else:
+            noise = torch.empty((n, 4), device=dev)
+            parts["torch normal_ (sampling noise, fresh every step)"] = lambda i: noise.normal_(generator=g)
+            if vn is not None and world > 1:
+                parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
+            parts["rollout_kernel<v2,policy>"] = lambda i: policy.forward(env.obs, noise, norm_stats=vn.stats if vn is not None else None)
+            parts["env_step_kernel<float,v2,rk4,moments>+moments_final"] = lambda i: env.step(policy.actions_clipped)
+    else:
+        u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
 
-    def policy_step(i):
-        if vn is not None:
-            vn.update_from_moments()                         # all-gather over ranks (N > 1) + Chan merge on device
-        policy.forward(env.obs, noise[i & 3], norm_stats=vn.stats if vn is not None else None)   # -> policy.actions_clipped
+        def regen(i):
+            u.uniform_(generator=g)
+            torch.addcmul(lo, u, span, out=a)
+        parts["torch uniform_ + addcmul (actions, fresh every step)"] = regen
+        parts[f"env_step_kernel<{'float' if args.precision == 'f32' else 'double'},v2,rk4>"] = lambda i: env.step(a)
 
     def one_step(i):
-        if policy is None:
-            env.step(ring[i & 3])
-        else:
-            policy_step(i)
-            env.step(policy.actions_clipped)
+        for fn in parts.values():
+            fn(i)
 
     def barrier():
         if world > 1:
@@ -286,8 +399,7 @@ def run_gpu(args) -> None:
     for i in range(args.warmup):
         one_step(i)
     barrier()
-    # CUDA-graph replay of the step loop (4 steps per graph, so the 4 action / noise buffers rotate exactly as in eager
-    # mode): removes the host launch path (Python -> ctypes -> cudaLaunch, ~5 launches per step) from the critical path
+    # CUDA-graph replay of the step loop (4 steps per graph): removes the host launch path (Python -> ctypes -> cudaLaunch)
     unroll = (4 if args.steps % 4 == 0 else 2 if args.steps % 2 == 0 else 1) if args.graph else 0   # exactly K steps are timed
     graph = None
     if unroll:
@@ -323,39 +435,30 @@ def run_gpu(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = n * world * args.steps / (ms_total / 1e3)
-
-    # ---- per-kernel durations for the roofline: a separate eager pass with CUDA events around each launch (untimed) ----
-    probe = 40
-    step_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(probe)]
-    policy_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(probe)]
-    for i in range(probe):
-        if policy is not None:
-            if vn is not None:
-                vn.update_from_moments()
-            policy_events[i][0].record()
-            policy.forward(env.obs, noise[i & 3], norm_stats=vn.stats if vn is not None else None)
-            policy_events[i][1].record()
-            step_events[i][0].record()
-            env.step(policy.actions_clipped)
-            step_events[i][1].record()
-        else:
-            step_events[i][0].record()
-            env.step(ring[i & 3])
-            step_events[i][1].record()
-    torch.cuda.synchronize()
-    step_kernel_ms = statistics.median(a.elapsed_time(b) for a, b in step_events)
-    if policy is None:
-        # bare-step workload: a step IS one launch of this kernel, so the graph-replayed step time is its duration without
-        # the host launch gap the event-bracketed eager pass includes
-        step_kernel_ms = min(step_kernel_ms, ms_total / args.steps)
-    policy_kernel_ms = statistics.median(a.elapsed_time(b) for a, b in policy_events) if policy is not None else None
+    if fused is not None and fused.status() != 0:
+        raise RuntimeError(f"rollout kernel: an internal hand-over timed out (code {fused.status()}); the timed region is invalid")
     if vn is not None and vn.exchange_failed():
         raise RuntimeError("peer-memory moment exchange timed out waiting for a rank; the timed region is invalid")
 
+    # ---- per-kernel durations for the roofline: each component alone, replayed from its own CUDA graph (no host launch gaps), on one
+    # rank at a time only where it has no rendezvous.  With one component the step IS the kernel.
+    kernel_ms = {}
+    ms_step = ms_total / args.steps
+    if len(parts) == 1:
+        kernel_ms[next(iter(parts))] = ms_step
+    else:
+        for name, fn in parts.items():
+            if name == "xchg_merge_kernel":
+                continue                                   # a rendezvous: its cost is the skew between ranks, reported as the remainder
+            kernel_ms[name] = graph_time(fn, 100, 4, dev)[0]
+        if "xchg_merge_kernel" in parts:
+            kernel_ms["xchg_merge_kernel (rendezvous: remainder of the step)"] = max(0.0, ms_step - sum(kernel_ms.values()))
+    barrier()
+
     # ---- end to end through the SB3-style VecEnv call: pinned host actions in, obs/reward/done out --------
     from rl_aerial_manipulator_b200.vec_env import QuadVecEnv
+    del graph
     env.close()
-    del ring
     venv = QuadVecEnv(n, env_version=2, precision=args.precision, substeps=args.substeps, device=local, seed=args.seed,
                       env_id_offset=rank * n, info_mode="lazy")
     obs = venv.reset()
@@ -391,43 +494,69 @@ def run_gpu(args) -> None:
 
     if rank == 0:
         peak, peak_src = measured_peak("hbm_gbs", 6650.0)
+        tpeak, tsrc = measured_peak("bf16_tflops_sustained", 1400.0)
         algo = ALGO_BYTES[("v2", args.precision)]
-        achieved = algo * n / (step_kernel_ms / 1e3) / 1e9
-        kname = f"env_step_kernel<{'float' if args.precision == 'f32' else 'double'},v2,rk4>"
-        step_roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(kname), "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo,
-                         "kernel_ms": step_kernel_ms}
-        roofline, roofline_other = step_roofline, []
-        if policy is not None and policy_kernel_ms > step_kernel_ms:
-            # the dominant kernel of this workload is the tcgen05 policy forward: algorithmic FLOPs (one float32 pass of the
-            # two MLPs; the split-float16 mode issues 3x that on the tensor pipe) against the measured dense bf16 GEMM rate
-            tpeak, tsrc = measured_peak("bf16_tflops_sustained", 1400.0)
-            tach = POLICY_FLOPS * n / (policy_kernel_ms / 1e3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "policy_forward_tc3_kernel<20,split-f16>", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
-                        "frac": tach / tpeak, "traffic": ncu_traffic("policy_forward_tc_kernel"), "peak_source": tsrc,
-                        "algorithmic_flops_per_env_step": POLICY_FLOPS, "kernel_ms": policy_kernel_ms,
-                        "note": "epilogue-bound: 512 tanh per env at 1.25 MUFU and 9 warp instructions each; ncu: issue slots 57 %, XU pipe 53 %, tensor pipe 34 % busy (three MMA->epilogue chains per SM)"}
-            roofline_other = [step_roofline]
+        traffic = ncu_traffic_table()
+        rl = []
+        for name, ms in kernel_ms.items():
+            if name.startswith("rollout_kernel"):
+                # the tcgen05 pipeline kernel: algorithmic FLOPs (one float32 pass of the two MLPs; the split-float16 mode issues 3x that
+                # on the tensor pipe) against the measured dense bf16 GEMM rate.  The fused variant also carries the env step's bytes.
+                tach = POLICY_FLOPS * n / (ms / 1e3) / 1e12
+                r = {"bound": "tensor", "kernel": name, "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                     "traffic": traffic.get(name), "peak_source": tsrc, "algorithmic_flops_per_env_step": POLICY_FLOPS, "kernel_ms": ms,
+                     "note": "bound by the epilogues (512 tanh per env: XU pipe + issue slots), not by the tensor pipe; the contract's "
+                             "bounds are hbm|tensor, so the fraction is quoted against the measured bf16 GEMM rate"}
+                if "fused" in name:
+                    hb = (algo + 80 + 16 + 4 + 4) * n / (ms / 1e3) / 1e9      # + obs read, sampled actions, value, log-prob written
+                    r["hbm_view"] = {"achieved": hb, "peak": peak, "unit": "GB/s", "frac": hb / peak,
+                                     "algorithmic_bytes_per_env_step": algo + 104}
+                rl.append(r)
+            elif name.startswith("env_step_kernel"):
+                ach = algo * n / (ms / 1e3) / 1e9
+                rl.append({"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                           "traffic": traffic.get(name), "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo, "kernel_ms": ms})
+            else:
+                rl.append({"kernel": name, "kernel_ms": ms})
+        rl.sort(key=lambda r: -r["kernel_ms"])
+        roofline = next((r for r in rl if "bound" in r), rl[0])
+        roofline_other = [r for r in rl if r is not roofline]
         base = None
+        extras = []
+        if world == 1 and not args.no_extras:
+            # the other single-GPU configurations of BASELINE.json (configs[2] and the float64 modes), short runs in the same process
+            for (en, prec, integ, st) in ((1 << 20, "f32", "rk4", 200), (1 << 20, "f64", "rk4", 100), (65536, "f32", "rk4", 400),
+                                         (65536, "f64", "rk4", 400), (65536, "f64", "lsoda", 6)):
+                if args.workload == "step" and en == n and prec == args.precision and integ == "rk4":
+                    continue
+                extras.append(step_extra(en, prec, integ, dev, args.seed, st))
         if world == 1 and not args.no_cpu_baseline:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], capture_output=True, text=True)
             try:
                 base = json.loads(r.stdout.strip().splitlines()[-1])
             except Exception:  # noqa: BLE001
                 base = {"error": (r.stderr or r.stdout)[-300:]}
+        ours = sum(1 for k in parts if not k.startswith("torch"))
+        if args.workload == "rollout" and args.rollout == "separate" and vn is not None:
+            ours += 1                                       # moments_final follows the step kernel
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": workload_name(args), "envs_per_gpu": n, "envs_total": n * world, "integrator": f"rk4x{args.substeps}",
-                           "vecnormalize": bool(vn is not None), "cuda_graph": bool(graph is not None),
-                           "actions": "policy (ppo_model_2300000_steps weights, stochastic, clipped)" if policy else "uniform-random over the action box, 4 pre-generated device buffers",
+                           "vecnormalize": bool(vn is not None), "cuda_graph": bool(unroll),
+                           "rollout": (args.rollout if args.workload == "rollout" else None),
+                           "actions": ("policy (ppo_model_2300000_steps weights), Gaussian noise drawn every step "
+                                       + ("inside the kernel (Philox4x32-10 on seed, global env id, step + Box-Muller)" if fused is not None else "by torch normal_ inside the timed region")
+                                       + ", clipped to the action box") if policy else "uniform-random over the action box, regenerated on the device every step inside the timed region",
                            "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
                            "parallelism": f"env-shard x{world}, no data-path collective",
                            "moment_exchange": vn.exchange if vn is not None else "none"},
-                "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": base,
+                "roofline": roofline, "roofline_other": roofline_other,
+                "kernels_ms": kernel_ms, "kernels_ms_sum": sum(kernel_ms.values()),
+                "extra": extras, "cpu_baseline": base,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                         "api": "QuadVecEnv.step(actions: np.ndarray) -> obs, rewards, dones, infos (pinned staging, info_mode=lazy)"},
-                "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
+                "gpu_launches": ours * args.steps, "clocks": clocks}
         emit(line)
     if world > 1:
         # no destroy_process_group(): tearing down a communicator that a captured CUDA graph still references can block;
@@ -452,6 +581,9 @@ def main():
     ap.add_argument("--vecnorm-exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: how ranks exchange the VecNormalize moments (peer = fused all-gather+merge kernel over NVLink peer memory)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step loop from a CUDA graph (4 steps per graph)")
+    ap.add_argument("--rollout", default="fused", choices=["fused", "separate"],
+                    help="rollout workload: one fused kernel per step (in-kernel Philox noise), or policy kernel + env-step kernel + torch normal_")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra single-GPU workload lines (configs[2], float64, LSODA)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -292,6 +292,42 @@ int qs_gae(const float* rewards, const float* values, const uint8_t* episode_sta
            void* stream);
 const char* qs_gae_last_error(void);
 
+/* PPO minibatch update -----------------------------------------------------------------------------------
+ * Replaces one minibatch of stable_baselines3 PPO.train() (inside model.learn(); reference call sites
+ * initial-implementation-v1/rl_train_vecN.py:13-36 -- batch_size 128, n_epochs 10, clip_range 0.2, ent_coef 0.01, lr 2e-4 -- and
+ * initial-implementation-v2/rl_train.py:38-56): advantage normalisation over the minibatch, evaluate_actions of the
+ * [128, 64, 64] Tanh actor and critic, clipped surrogate + vf_coef * MSE + ent_coef * entropy loss, backward, global-norm
+ * clipping, torch.optim.Adam(eps 1e-5) -- ONE kernel launch, float32, deterministic (fixed reduction order).
+ *   params        device f32[qs_ppo_n_params(obs_dim)], the qs_policy_forward blob; updated in place
+ *   obs/actions/old_logp/advantages/returns   flat device rollout buffers f32[total, obs_dim] / [total, 4] / [total] x 3
+ *   idx           device i64[B] rows of this minibatch (a slice of the epoch's permutation), or NULL = rows 0..B-1
+ *   stats_out     device f32[8] or NULL: loss, policy_gradient_loss, value_loss, entropy_loss, grad_norm (before clipping),
+ *                 clip_fraction, approx_kl, B
+ * The handle owns the Adam moments and step count (device resident: the call is CUDA-graph capturable).  Several ranks:
+ * qs_ppo_grad (gradient of the local minibatch -> grad_out f32[n_params], or the handle's own buffer if NULL), average over
+ * ranks (NCCL all-reduce), qs_ppo_apply (clipping + Adam on the averaged gradient; grad NULL = the handle's buffer).
+ */
+typedef struct qs_ppo qs_ppo;
+typedef struct qs_ppo_hyper {
+    float clip_range, ent_coef, vf_coef, max_grad_norm;
+    float lr, beta1, beta2, adam_eps;
+    int32_t normalize_advantage, reserved;
+} qs_ppo_hyper;
+void qs_ppo_default_hyper(qs_ppo_hyper* hp); /* SB3 defaults: 0.2, 0, 0.5, 0.5, 3e-4, 0.9, 0.999, 1e-5, normalise */
+int qs_ppo_n_params(int obs_dim);            /* floats in the parameter blob (17 or 20 observations), -1 otherwise */
+int qs_ppo_create(int device, int obs_dim, qs_ppo** out);
+int qs_ppo_destroy(qs_ppo* o);
+int qs_ppo_update(qs_ppo* o, float* params, const float* obs, const float* actions, const float* old_logp,
+                  const float* advantages, const float* returns, const int64_t* idx, int64_t B, const qs_ppo_hyper* hp,
+                  float* stats_out, void* stream);
+int qs_ppo_grad(qs_ppo* o, const float* params, const float* obs, const float* actions, const float* old_logp,
+                const float* advantages, const float* returns, const int64_t* idx, int64_t B, const qs_ppo_hyper* hp,
+                float* grad_out, float* stats_out, void* stream);
+int qs_ppo_apply(qs_ppo* o, float* params, const float* grad, const qs_ppo_hyper* hp, float* stats_out, void* stream);
+/* device pointers of the optimizer state (checkpointing, tests): Adam m, v f32[n_params], step i64[1], gradient buffer */
+int qs_ppo_state(qs_ppo* o, float** m, float** v, long long** step, float** grad);
+const char* qs_ppo_last_error(void);
+
 /* Peer-memory exchange of the VecNormalize moments (multi-GPU) --------------------------------------------
  * The only exchange step of the sharded env path is the 2d+1 doubles (n, mean[d], M2[d]) each rank contributes to the running
  * statistics per step.  qs_xchg_merge is that all-gather FUSED with the Chan merge in one kernel over NVLink peer memory: the

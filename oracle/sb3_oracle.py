@@ -104,3 +104,22 @@ def merge_moments(stats, moments):
         var = M2 / tot
         count = tot
     return torch.cat([count.reshape(1), mean, var])
+
+
+def torch_policy_forward(state_dict, obs, dtype=None):
+    """Plain torch forward of SB3's MlpPolicy (mlp_extractor policy_net / value_net: Linear-Tanh x 3, then action_net / value_net)
+    on `obs`'s device -- the float32 (or float64) checker of the CUDA policy kernels.  `state_dict`: name -> numpy array, the
+    names of the policy.pth inside an SB3 zip.  Returns (mean[n,4], value[n])."""
+    import torch
+
+    dtype = dtype or torch.float32
+    sd = {k: torch.from_numpy(np.asarray(v)).to(obs.device, dtype) for k, v in state_dict.items()}
+    x = obs.to(dtype)
+
+    def mlp(x, net):
+        for i in (0, 2, 4):
+            x = torch.tanh(x @ sd[f"mlp_extractor.{net}.{i}.weight"].T + sd[f"mlp_extractor.{net}.{i}.bias"])
+        return x
+    mean = mlp(x, "policy_net") @ sd["action_net.weight"].T + sd["action_net.bias"]
+    value = (mlp(x, "value_net") @ sd["value_net.weight"].T + sd["value_net.bias"])[:, 0]
+    return mean, value

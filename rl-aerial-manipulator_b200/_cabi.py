@@ -97,6 +97,13 @@ class QsRolloutArgs(C.Structure):
 SAMPLE_MEAN, SAMPLE_NOISE, SAMPLE_PHILOX = 0, 1, 2
 
 
+class QsPpoHyper(C.Structure):
+    """qs_ppo_hyper of include/quadsim.h."""
+    _fields_ = [("clip_range", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float), ("max_grad_norm", C.c_float),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("normalize_advantage", C.c_int32), ("reserved", C.c_int32)]
+
+
 class QsPidGains(C.Structure):
     """qs_pid_gains of include/quadsim.h (order x, y, z, phi, theta, psi)."""
     _fields_ = [("kp", C.c_double * 6), ("kd", C.c_double * 6), ("ki", C.c_double * 6), ("max_integral", C.c_double)]
@@ -142,6 +149,19 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.qs_rollout_step.argtypes = [vp, C.POINTER(QsRolloutArgs), vp]
     lib.qs_rollout_step.restype = C.c_int
     lib.qs_rollout_status.restype = C.c_int
+    lib.qs_ppo_default_hyper.argtypes = [C.POINTER(QsPpoHyper)]
+    lib.qs_ppo_default_hyper.restype = None
+    lib.qs_ppo_n_params.argtypes = [i32]
+    lib.qs_ppo_n_params.restype = C.c_int
+    lib.qs_ppo_create.argtypes = [i32, i32, C.POINTER(vp)]
+    lib.qs_ppo_destroy.argtypes = [vp]
+    lib.qs_ppo_update.argtypes = [vp] * 8 + [i64, C.POINTER(QsPpoHyper), vp, vp]
+    lib.qs_ppo_grad.argtypes = [vp] * 8 + [i64, C.POINTER(QsPpoHyper), vp, vp, vp]
+    lib.qs_ppo_apply.argtypes = [vp, vp, vp, C.POINTER(QsPpoHyper), vp, vp]
+    lib.qs_ppo_state.argtypes = [vp] + [C.POINTER(vp)] * 4
+    lib.qs_ppo_last_error.restype = C.c_char_p
+    for name in ("qs_ppo_create", "qs_ppo_destroy", "qs_ppo_update", "qs_ppo_grad", "qs_ppo_apply", "qs_ppo_state"):
+        getattr(lib, name).restype = C.c_int
     lib.qs_pid_default_gains.argtypes = [C.POINTER(QsPidGains)]
     lib.qs_pid_default_gains.restype = None
     lib.qs_pid_run.argtypes = [vp, C.POINTER(QsPidGains), C.c_double] + [vp] * 8 + [i32, vp]

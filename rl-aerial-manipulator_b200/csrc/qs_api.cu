@@ -234,6 +234,12 @@ int qs_step(qs_handle* h, const float* actions, float* obs_out, void* reward_out
     if (!h) { set_error(nullptr, "qs_step: null handle"); return QS_EINVAL; }
     if (!actions || !obs_out || !reward_out || !flags_out) { set_error(h, "qs_step: actions, obs_out, reward_out and flags_out are required"); return QS_EINVAL; }
     if (!h->initialized) { set_error(h, "qs_step: call qs_reset first"); return QS_EINVAL; }
+    // the kernels read an action row with one LDG.128 and write obs rows with STG.128: a misaligned pointer would be a sticky
+    // misaligned-address fault instead of an error code
+    if ((reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(obs_out)) & 15) {
+        set_error(h, "qs_step: actions and obs_out must be 16-byte aligned");
+        return QS_EINVAL;
+    }
     QS_CUDA(h, cudaSetDevice(h->cfg.device));
     int rc = QS_OK;
     if (h->cfg.precision == QS_F32)

@@ -7,7 +7,7 @@
 // Step s (1, 2, ...; the counter lives in device memory so a captured graph replays correctly), parity p = s & 1:
 //   1. thread c < len stores local[c] into slots[p][rank][c] of EVERY rank's buffer (its own included), then fences system-wide;
 //   2. one thread publishes flags[p][rank] = s in every buffer (after the CTA barrier, so all data stores are fenced);
-//   3. every thread acquire-spins until its own buffer's flags[p][q] >= s for all q (bounded: ~10 s, then a sticky error);
+//   3. thread q acquire-spins until its own buffer's flags[p][q] >= s (bounded: ~10 s, then a sticky error), CTA barrier;
 //   4. Chan merge of slots[p][0..world) in rank order into the running statistics.
 // Two parities suffice: a rank can only reach step s+2 after every rank has published step s+1, which each rank does after it
 // finished reading step s.
@@ -76,22 +76,28 @@ __global__ void __launch_bounds__(128) xchg_merge_kernel(void* const* __restrict
     // 3. wait for everybody's triplet of this step in the local buffer
     const double* my_slots = reinterpret_cast<const double*>(peers[rank]);
     const unsigned long long* my_flags = reinterpret_cast<const unsigned long long*>(my_slots + slot_doubles) + (size_t)par * world;
-    bool ok = true;
-    const long long t0 = clock64();
-    for (int q = 0; q < world; ++q) {
-        while (ld_acquire_sys(my_flags + q) < s) {
+    // one decision per source rank (thread q waits for rank q), shared by all columns: after a timeout every column merges the
+    // same set of ranks, so the statistics stay self-consistent and the sticky flag says they are incomplete
+    __shared__ int s_arrived[64];
+    if (c < world) {
+        bool ok = true;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(my_flags + c) < s) {
             if (clock64() - t0 > 20000000000ll) { ok = false; break; }  // ~10 s at 1.9 GHz: ranks may be seconds apart at start-up
             __nanosleep(64);
         }
+        s_arrived[c] = ok ? 1 : 0;
+        if (!ok) *failed = 1;
     }
-    if (!ok && c == 0) *failed = 1;
+    __syncthreads();
     // 4. Chan merge in rank order (RunningMeanStd.update_from_moments, k batches) -- same arithmetic as vecnorm_merge_kernel
     double count = 0.0, mean = 0.0, var = 0.0;
     if (c < d) {
         count = stats[0]; mean = stats[1 + c]; var = stats[1 + d + c];
         for (int q = 0; q < world; ++q) {
             const volatile double* m = my_slots + ((size_t)par * world + q) * len;   // written by a peer: never from a stale L1 line
-            if (ld_acquire_sys(my_flags + q) < s) continue;             // timed out: skip what never arrived
+            if (!s_arrived[q]) continue;                                // timed out: skip what never arrived
+            (void)ld_acquire_sys(my_flags + q);                         // acquire in THIS thread before reading the peer's data
             const double bn = m[0];
             if (bn <= 0.0) continue;
             const double delta = m[1 + c] - mean;

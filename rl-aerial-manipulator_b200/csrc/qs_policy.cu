@@ -255,6 +255,11 @@ int qs_policy_forward(const float* params, int obs_dim, const float* obs, const 
         return QS_EINVAL;
     }
     if (n == 0) return QS_OK;
+    if ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(actions) |
+         reinterpret_cast<uintptr_t>(actions_clipped) | reinterpret_cast<uintptr_t>(obs_norm_out)) & 15) {
+        snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward: obs, noise, actions, actions_clipped and obs_norm_out must be 16-byte aligned");
+        return QS_EINVAL;
+    }
     if (impl < 0 || impl > 5) {
         snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward: impl must be one of QS_POLICY_*");
         return QS_EINVAL;

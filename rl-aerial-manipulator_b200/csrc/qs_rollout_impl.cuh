@@ -107,6 +107,20 @@ static_assert(SM_X % 128 == 0 && SM_ONE % 128 == 0, "operand tiles are 128-byte 
 
 __device__ int g_ro_status;          // sticky: != 0 after a bounded wait expired (role * 100 + barrier index + 1)
 
+// Development aid (-DQS_RO_TRACE=1, tools/rollout_trace.py): lane 0 of every warp of CTA 0 logs (event code, clock) pairs, so the
+// hand-over latencies between the roles can be read off a real run.  Compiled out of the product build.
+#ifdef QS_RO_TRACE
+constexpr int TRACE_LEN = 2048;
+__device__ uint2 g_ro_trace[32][TRACE_LEN];
+#define RO_TRACE_INIT() uint2* tr_buf = g_ro_trace[threadIdx.x >> 5]; int tr_n = 0; const bool tr_on = blockIdx.x == 0 && (threadIdx.x & 31) == 0
+#define RO_TRACE(code) do { if (tr_on && tr_n < TRACE_LEN - 1) tr_buf[tr_n++] = make_uint2((uint32_t)(code), (uint32_t)clock64()); } while (0)
+#define RO_TRACE_END() do { if (tr_on) tr_buf[TRACE_LEN - 1] = make_uint2((uint32_t)tr_n, 0u); } while (0)
+#else
+#define RO_TRACE_INIT() do { } while (0)
+#define RO_TRACE(code) do { } while (0)
+#define RO_TRACE_END() do { } while (0)
+#endif
+
 struct RoParams {
     // policy
     const unsigned char* image;      // prepared operand image (IMG_BYTES), or null -> stage from `params`
@@ -288,6 +302,7 @@ __device__ __forceinline__ void role_mma(const Ctx& c, int slot) {
     const int role = 300 + slot * 50;
     uint32_t job = 0;
     bool l1_issued = false;
+    RO_TRACE_INIT();
     for (int i = slot; i < c.cnt; i += 2) {
         const int xb = i % XBUFS;
 #pragma unroll 1
@@ -304,6 +319,7 @@ __device__ __forceinline__ void role_mma(const Ctx& c, int slot) {
                     if (net == 1) umma_commit(c.bar(B_XFREE + xb));
                 }
                 __syncwarp();
+                RO_TRACE(0x200000u | job);
             }
             l1_issued = false;
             // ---- layer 2: bias k-step, then the chunks of H1 as the epilogue warps deliver them
@@ -312,6 +328,7 @@ __device__ __forceinline__ void role_mma(const Ctx& c, int slot) {
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 if (!mbar_wait_bounded(c.bar(B_H1 + slot * 4 + ch), par, role + B_H1 + 1)) return;
+                RO_TRACE(0x210000u | (ch << 12) | job);
                 tc_fence_after();
                 if (elect_one()) {
                     issue_chunk(d2, d1, ch, w2h, w2l);
@@ -319,6 +336,7 @@ __device__ __forceinline__ void role_mma(const Ctx& c, int slot) {
                 }
                 __syncwarp();
             }
+            RO_TRACE(0x220000u | job);
             // ---- layer 1 of the NEXT job right behind (MMAs execute in issue order: D1 is free once layer 2 has read it) -- unless it
             // needs an X tile the env warps have not staged yet: then layer 3 of this job goes first (no head-of-line blocking)
             int nxb = xb, nnet = 1, ni = i;
@@ -335,15 +353,18 @@ __device__ __forceinline__ void role_mma(const Ctx& c, int slot) {
                 }
                 __syncwarp();
                 l1_issued = true;
+                RO_TRACE(0x230000u | job);
             }
             // ---- layer 3 (D3 is free once the epilogue warps have loaded the previous job's layer-3 result)
             if (!mbar_wait_bounded(c.bar(B_D3FREE + slot), par ^ 1u, role + B_D3FREE + 1)) return;
+            RO_TRACE(0x240000u | job);
             tc_fence_after();
             if (elect_one()) issue_bias(c, d3, w3h, w3l, N2 / 16);
             __syncwarp();
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 if (!mbar_wait_bounded(c.bar(B_H2 + slot * 2 + ch), par, role + B_H2 + 1)) return;
+                RO_TRACE(0x250000u | (ch << 12) | job);
                 tc_fence_after();
                 if (elect_one()) {
                     issue_chunk(d3, d2, ch, w3h, w3l);
@@ -351,8 +372,10 @@ __device__ __forceinline__ void role_mma(const Ctx& c, int slot) {
                 }
                 __syncwarp();
             }
+            RO_TRACE(0x260000u | job);
         }
     }
+    RO_TRACE_END();
 }
 // the first job of a slot issues the critic's L1 from inside the loop above (net == 0 -> next job is net 1 of the same tile), so
 // the X buffer of that tile is released there too.
@@ -392,6 +415,7 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
     const int row = quad * 32 + lane;
     uint32_t job = 0;
     float mean[NACT] = {0.f, 0.f, 0.f, 0.f};
+    RO_TRACE_INIT();
     for (int i = slot; i < c.cnt; i += 2) {
         const uint32_t k = (uint32_t)i >> 1;
 #pragma unroll 1
@@ -404,13 +428,16 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
                 if (ch == half && !mbar_wait_bounded(c.bar(B_D1 + slot), par, role + B_D1 + 1)) return;
                 if (ch == 4 + half && !mbar_wait_bounded(c.bar(B_D2 + slot), par, role + B_D2 + 1)) return;
                 if (ch == half || ch == 4 + half) tc_fence_after();
+                RO_TRACE(0x100000u | (ch << 12) | job);
                 chunk_tanh_split(tm + 32u * (uint32_t)ch);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(c.bar(ch < 4 ? B_H1 + slot * 4 + ch : B_H2 + slot * 2 + (ch - 4)));
+                RO_TRACE(0x110000u | (ch << 12) | job);
             }
             if (!mbar_wait_bounded(c.bar(B_D3 + slot), par, role + B_D3 + 1)) return;
+            RO_TRACE(0x130000u | job);
             tc_fence_after();
             float o[NACT];                                               // partial head sums of this warp's chunks (+ bias in half 0)
 #pragma unroll
@@ -438,6 +465,7 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
                     }
                 }
             }
+            RO_TRACE(0x140000u | job);
             if (net == 0) {
 #pragma unroll
                 for (int j = 0; j < NACT; ++j) mean[j] = o[j];
@@ -450,6 +478,7 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
             }
         }
     }
+    RO_TRACE_END();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -570,9 +599,12 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int pa
         if (par < c.cnt && e0 < p.n) pool_load<float, VER>(sp.pool, sp.n, e0, s_nx);
     }
     // the X tile of local tile i + 2 is staged before tile i is stepped; the first iteration(s) only stage (one call site: code size)
+    RO_TRACE_INIT();
 #pragma unroll 1
     for (int i = par - 2; i < c.cnt; i += STRIDE) {
+        RO_TRACE(0x300000u | (uint32_t)(i + 2));
         if (i + 2 < c.cnt && !stage_x<OBS>(c, p, i + 2, quad, lane, smem, s_norm)) return;
+        RO_TRACE(0x310000u | (uint32_t)(i + 2));
         if (i < 0) continue;
         const int slot = i & 1;
         const uint32_t k = (uint32_t)i >> 1;
@@ -593,6 +625,7 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int pa
             }
         }
         if (!mbar_wait_bounded(c.bar(B_OUTF + slot * 4 + quad), k & 1u, 200 + B_OUTF + 1)) return;
+        RO_TRACE(0x320000u | (uint32_t)i);
         float4 mu = s_mean[slot * EPI_SPLIT * ROWS + row];
         float value = s_val[slot * EPI_SPLIT * ROWS + row];
 #pragma unroll
@@ -678,6 +711,7 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int pa
         }
     }
     if (moments && lane < OBS) { s_mom[lane] = m1; s_mom[OBS + lane] = m2; }
+    RO_TRACE_END();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -909,6 +943,18 @@ int policy_pipeline_status() {
     return v;
 }
 #endif  // QS_RO_BUILD_POLICY
+}  // namespace qs
+#ifdef QS_RO_TRACE
+#ifdef QS_RO_BUILD_POLICY
+extern "C" int qs_trace_dump_policy(void* out, int bytes) {
+#else
+extern "C" int qs_trace_dump_fused(void* out, int bytes) {
+#endif
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, qs::QS_RO_NS::g_ro_trace, bytes < (int)sizeof(qs::QS_RO_NS::g_ro_trace) ? bytes : sizeof(qs::QS_RO_NS::g_ro_trace));
+}
+#endif
+namespace qs {
 
 #ifdef QS_RO_BUILD_FUSED
 int policy_pipeline_status();

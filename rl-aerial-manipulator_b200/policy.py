@@ -57,6 +57,27 @@ def pack_params(sd: dict, obs_dim: int) -> np.ndarray:
     return np.concatenate(parts).astype(np.float32)
 
 
+def unpack_params(blob: np.ndarray, obs_dim: int) -> dict:
+    """Inverse of pack_params: the blob -> an SB3-named state_dict (float32)."""
+    blob = np.asarray(blob, dtype=np.float32)
+    sd, o = {}, 0
+
+    def take(n):
+        nonlocal o
+        v = blob[o:o + n]
+        o += n
+        return v
+    for net, head, n_out in (("policy_net", "action_net", NACT), ("value_net", "value_net", 1)):
+        for i, (k_in, k_out) in zip((0, 2, 4), ((obs_dim, H1), (H1, H2), (H2, H3))):
+            sd[f"mlp_extractor.{net}.{i}.weight"] = take(k_in * k_out).reshape(k_in, k_out).T.copy()
+            sd[f"mlp_extractor.{net}.{i}.bias"] = take(k_out).copy()
+        sd[f"{head}.weight"] = take(H3 * NACT).reshape(H3, NACT)[:, :n_out].T.copy()
+        sd[f"{head}.bias"] = take(NACT)[:n_out].copy()
+    sd["log_std"] = take(NACT).copy()
+    assert o == blob.size
+    return sd
+
+
 IMPL = {"auto": 0, "fp32": 1, "tensor": 2, "tensor_fast": 3, "tensor_pipeline": 4, "tensor_chains": 5}
 
 
@@ -196,16 +217,3 @@ class MlpPolicyKernel:
         for st in self._chunk_streams:
             st.synchronize()
         return h_act.numpy()
-
-    # ---- plain torch reference (tests only use it as the fp32 checker) ------------------------------
-    def torch_reference(self, obs: torch.Tensor, dtype=torch.float32):
-        sd = {k: torch.from_numpy(v).to(obs.device, dtype) for k, v in self.state_dict.items()}
-        x = obs.to(dtype)
-
-        def mlp(x, net):
-            for i in (0, 2, 4):
-                x = torch.tanh(x @ sd[f"mlp_extractor.{net}.{i}.weight"].T + sd[f"mlp_extractor.{net}.{i}.bias"])
-            return x
-        mean = mlp(x, "policy_net") @ sd["action_net.weight"].T + sd["action_net.bias"]
-        value = (mlp(x, "value_net") @ sd["value_net.weight"].T + sd["value_net.bias"])[:, 0]
-        return mean, value

@@ -44,11 +44,22 @@ class _Bag:
         self.__dict__.update(st)
 
 
+# What a VecNormalize pickle may reference besides SB3 / gymnasium classes (which become attribute bags): numpy's array /
+# scalar / dtype reconstructors and a few plain containers.  Anything else (os.system, builtins.eval, ...) is refused: a
+# vec_normalize.pkl from a model zoo is untrusted input.
+_NUMPY_OK = {"_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer", "float64", "float32", "int64", "int32", "bool_", "uint8"}
+_PLAIN_OK = {("collections", "OrderedDict"), ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "slice"),
+             ("builtins", "complex"), ("builtins", "bytearray"), ("_codecs", "encode")}
+
+
 class _TolerantUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.split(".")[0] in ("stable_baselines3", "gymnasium", "gym"):
+        top = module.split(".")[0]
+        if top in ("stable_baselines3", "gymnasium", "gym"):
             return type(name, (_Bag,), {"__module__": module})
-        return super().find_class(module, name)
+        if (top == "numpy" and name in _NUMPY_OK) or (module, name) in _PLAIN_OK:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"vec_normalize pickle references {module}.{name}, which is not on the allowlist")
 
 
 def load_vecnormalize_pkl(path: str) -> dict:
@@ -117,6 +128,9 @@ def save_vecnormalize_pkl(path: str, state: dict, num_envs: int, obs_dim: int) -
              "clip_reward": float(state.get("clip_reward", 10.0)), "gamma": float(state.get("gamma", 0.99)),
              "epsilon": float(state.get("epsilon", 1e-8)), "training": bool(state.get("training", True)),
              "norm_reward": bool(state.get("norm_reward", False)), "old_reward": np.zeros(num_envs), "old_obs": np.zeros((num_envs, obs_dim), np.float32)}
+        if not issubclass(VN, _Bag):
+            # the real SB3 class: its __getstate__ deletes these three from a copy of __dict__ before pickling
+            d.update(venv=None, class_attributes={}, returns=np.zeros(num_envs))
         with open(path, "wb") as f:
             pickle.dump(bag(VN, d), f, protocol=4)
 

@@ -59,7 +59,7 @@ def test_policy_forward_stochastic_vs_oracle(golden_dir, n, impl):
     np.testing.assert_allclose(t2n(v[:m]), vo, rtol=0, atol=tol_v)
     np.testing.assert_allclose(t2n(lp[:m]), lpo, rtol=1e-5, atol=1e-5)
     # whole batch against the plain torch fp32 reference of the same op
-    mean_t, value_t = pol.torch_reference(obs)
+    mean_t, value_t = so.torch_policy_forward(pol.state_dict, obs)
     a_t = mean_t + torch.exp(torch.from_numpy(pol.state_dict["log_std"]).cuda()) * noise
     assert (a - a_t).abs().max() < tol_a and (v - value_t).abs().max() < tol_v
     assert torch.equal(pol.actions_clipped, torch.minimum(torch.maximum(a, torch.tensor([0.0, -1, -1, -1], device="cuda")),

@@ -151,3 +151,57 @@ def test_quad_vecnormalize_wrapper_vs_oracle(tmp_path):
     np.testing.assert_array_equal(vn2.obs_rms.mean, vn.obs_rms.mean)
     vn.close()
     vn2.close()
+
+
+def test_vecnormalize_pkl_with_a_real_sb3_class_on_the_path(tmp_path, golden_dir, monkeypatch):
+    """When stable_baselines3 is importable the writer uses its classes; SB3's VecNormalize.__getstate__ deletes `venv`,
+    `class_attributes` and `returns` from the state, so they have to be there."""
+    import sys
+    import types
+
+    from rl_aerial_manipulator_b200 import sb3_compat as sc
+
+    class VecNormalize:                       # the relevant part of SB3 2.6.0's class
+        def __getstate__(self):
+            state = self.__dict__.copy()
+            del state["venv"]
+            del state["class_attributes"]
+            del state["returns"]
+            return state
+
+        def __setstate__(self, state):
+            self.__dict__.update(state)
+            self.venv = None
+
+    class RunningMeanStd:
+        pass
+
+    for mn in ("stable_baselines3", "stable_baselines3.common", "stable_baselines3.common.vec_env", sc._SB3_VN, sc._SB3_RMS):
+        monkeypatch.setitem(sys.modules, mn, types.ModuleType(mn))
+    VecNormalize.__module__, RunningMeanStd.__module__ = sc._SB3_VN, sc._SB3_RMS
+    VecNormalize.__qualname__, RunningMeanStd.__qualname__ = "VecNormalize", "RunningMeanStd"
+    sys.modules[sc._SB3_VN].VecNormalize = VecNormalize
+    sys.modules[sc._SB3_RMS].RunningMeanStd = RunningMeanStd
+    z = np.load(os.path.join(golden_dir, "vecnorm_v1.npz"))
+    p = str(tmp_path / "vn.pkl")
+    sc.save_vecnormalize_pkl(p, {k: z[k] for k in z.files}, num_envs=8, obs_dim=17)
+    back = sc.load_vecnormalize_pkl(p)
+    np.testing.assert_array_equal(back["obs_var"], z["obs_var"])
+    names = [arg for op, arg, _ in pickletools.genops(open(p, "rb").read()) if op.name == "SHORT_BINUNICODE"]
+    assert "venv" not in names and "returns" not in names          # SB3's own pickles do not carry them either
+
+
+def test_vecnormalize_pkl_reader_refuses_foreign_globals(tmp_path):
+    import pickle
+
+    from rl_aerial_manipulator_b200 import sb3_compat as sc
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("true",))
+    p = str(tmp_path / "evil.pkl")
+    with open(p, "wb") as f:
+        pickle.dump({"obs_rms": Evil()}, f)
+    with pytest.raises(pickle.UnpicklingError, match="allowlist"):
+        sc.load_vecnormalize_pkl(p)

@@ -11,7 +11,7 @@ for n in (128, 256, 1000, 65536, 1 << 20):
     noise = torch.randn((n, 4), device="cuda", generator=g)
     pf = MlpPolicyKernel.from_npz(path, device="cuda", impl="fp32")
     a0, v0, l0 = [x.clone() for x in pf.forward(obs, noise)]
-    m64, v64 = pf.torch_reference(obs[:4096], torch.float64)
+    m64, v64 = so.torch_policy_forward(pf.state_dict, obs[:4096], torch.float64)
     a64 = m64 + torch.exp(torch.from_numpy(pf.state_dict["log_std"]).cuda().double()) * noise[:4096].double()
     print(n, "fp32 vs f64: da", float((a0[:4096] - a64).abs().max()), "dv", float((v0[:4096] - v64).abs().max()), flush=True)
     pols = {"fp32": pf}

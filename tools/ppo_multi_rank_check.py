@@ -25,7 +25,7 @@ logs = []
 ppo.learn(2 * 32 * n * world, log=logs.append)
 torch.cuda.synchronize()
 el = time.time() - t0
-for name, t in (("params", ppo.net.packed()), ("obs_rms", vn.obs_rms.stats)):
+for name, t in (("params", ppo.policy.params), ("obs_rms", vn.obs_rms.stats)):
     allt = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(allt, t.contiguous())
     assert all(torch.equal(allt[0], x) for x in allt), f"{name} differ across ranks"

@@ -293,20 +293,19 @@ def step_extra(n, precision, integrator, dev, seed, steps):
     from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
     env = BatchedQuadEnv(n, env_version=2, precision=precision, integrator=integrator, device=dev.index, seed=seed)
     env.reset()
-    g = torch.Generator(device=dev).manual_seed(seed)
     lo = torch.tensor([0.0, -1, -1, -1], device=dev)
     span = torch.tensor([2.0, 2, 2, 2], device=dev)
     u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
-    many = integrator == "rk4" and hasattr(env, "step_many")
+    many = integrator == "rk4" and n <= (1 << 18)         # small batches: T steps per launch (the launch is the floor there)
     T = 16
     if many:
         # T steps per launch, state in registers, uniform actions drawn in the kernel (Philox on (seed, global env id, step))
-        ms, graph = graph_time(lambda i: env.step_many(T), steps, 1, dev)
+        ms, graph = graph_time(lambda i: env.step_many(T, update_obs=False), max(1, steps // T), 1, dev)
         ms /= T
         launches, actions = 1.0 / T, f"in-kernel Philox uniform over the action box, {T} steps per launch (qs_step_many)"
     else:
         def one(i):
-            u.uniform_(generator=g)
+            u.uniform_()
             torch.addcmul(lo, u, span, out=a)
             env.step(a)
         ms, graph = graph_time(one, steps, 4 if integrator == "rk4" else 1, dev)
@@ -314,15 +313,22 @@ def step_extra(n, precision, integrator, dev, seed, steps):
     del graph
     env.close()
     algo = ALGO_BYTES[("v2", precision)]
+    note = ("parity mode: adaptive LSODA, ~35 divergent f-evals per step -- latency-bound, not a throughput mode" if integrator == "lsoda" else
+            ("working set fits the 126 MB L2" if n * 185 < 126e6 else "working set exceeds L2"))
+    if many:
+        # the state record crosses HBM once per T steps: what is left per env-step is the rollout record (obs 80 B + reward + flags)
+        rsz = 4 if precision == "f32" else 8
+        state = (84 if precision == "f32" else 160) * 2
+        algo = 80 + rsz + 1 + state / T
+        note = (f"T = {T} steps per launch: {algo:.1f} algorithmic B per env-step (single-step kernel: {ALGO_BYTES[('v2', precision)]} B); the mode is "
+                "bound by the RK4 dependency chains at ~14 warps per SM, not by HBM")
     peak, peak_src = measured_peak("hbm_gbs", 6650.0)
     ach = algo * n / (ms / 1e3) / 1e9
     tag = f"{n // (1 << 20)}M" if n % (1 << 20) == 0 else str(n)
     return {"workload": f"v2_step_{tag}_{precision}" + ("_lsoda" if integrator == "lsoda" else ""), "value": n / (ms / 1e3), "unit": UNIT,
             "ms_per_step": ms, "dtype": precision, "integrator": integrator, "actions": actions, "our_launches_per_step": launches,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": algo,
-                         "note": ("parity mode: adaptive LSODA, ~35 divergent f-evals per step -- latency-bound, not a throughput mode" if integrator == "lsoda" else
-                                  ("working set fits the 126 MB L2" if n * 185 < 126e6 else "working set exceeds L2"))}}
+                         "algorithmic_bytes_per_env_step": algo, "note": note}}
 
 
 def run_gpu(args) -> None:
@@ -348,10 +354,40 @@ def run_gpu(args) -> None:
                          device=local, env_id_offset=rank * n, seed=args.seed)
     env.reset()
     policy = vn = fused = None
-    g = torch.Generator(device=dev).manual_seed(args.seed + rank)
+    torch.cuda.manual_seed(args.seed + rank)          # torch's default CUDA generator: its Philox offset advances under graph replay
     lo = torch.tensor([0.0, -1, -1, -1], device=dev)
     span = torch.tensor([2.0, 2, 2, 2], device=dev)
-    parts = {}                          # name -> callable(i): the launches of one step, by kernel, for the per-kernel timing
+    fused_holder = {}
+
+    def build_parts(mode):
+        """name -> callable(i): the launches of one step, by kernel (also the unit of the per-kernel timing)."""
+        parts = {}
+        if args.workload == "rollout":
+            if mode == "fused":
+                from rl_aerial_manipulator_b200.rollout import FusedRollout
+                # ONE kernel per step: normalise -> tcgen05 policy forward -> in-kernel Philox Gaussian sampling -> clip -> env step ->
+                # auto-reset -> moments (+ merge on one GPU)
+                fused_holder["f"] = FusedRollout(env, policy, vecnorm=vn, sample="philox", noise_seed=args.seed)
+                parts["rollout_kernel<v2,fused>"] = lambda i: fused_holder["f"].step()
+                if vn is not None and world > 1:
+                    parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
+            else:
+                noise = torch.empty((n, 4), device=dev)
+                parts["torch normal_ (sampling noise, fresh every step)"] = lambda i: noise.normal_()
+                if vn is not None and world > 1:
+                    parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
+                parts["rollout_kernel<v2,policy>"] = lambda i: policy.forward(env.obs, noise, norm_stats=vn.stats if vn is not None else None)
+                parts["env_step_kernel<float,v2,rk4,moments>+moments_final"] = lambda i: env.step(policy.actions_clipped)
+        else:
+            u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
+
+            def regen(i):
+                u.uniform_()
+                torch.addcmul(lo, u, span, out=a)
+            parts["torch uniform_ + addcmul (actions, fresh every step)"] = regen
+            parts[f"env_step_kernel<{'float' if args.precision == 'f32' else 'double'},v2,rk4>"] = lambda i: env.step(a)
+        return parts
+
     if args.workload == "rollout":
         from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
         from rl_aerial_manipulator_b200.vec_normalize import DeviceRunningMeanStd
@@ -362,29 +398,8 @@ def run_gpu(args) -> None:
             # per rank over NVLink peer memory) and the Chan merge (qs_xchg_merge; NCCL all-gather + merge kernel as fallback)
             vn = DeviceRunningMeanStd(env.obs_dim, dev, exchange=args.vecnorm_exchange)
             vn.attach(env, merge=(world == 1))
-        if args.rollout == "fused":
-            from rl_aerial_manipulator_b200.rollout import FusedRollout
-            # ONE kernel per step: normalise -> tcgen05 policy forward -> in-kernel Philox Gaussian sampling -> clip -> env step ->
-            # auto-reset -> moments (+ merge on one GPU)
-            fused = FusedRollout(env, policy, vecnorm=vn, sample="philox", noise_seed=args.seed)
-            parts["rollout_kernel<v2,fused>"] = lambda i: fused.step()
-            if vn is not None and world > 1:
-                parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
-        else:
-            noise = torch.empty((n, 4), device=dev)
-            parts["torch normal_ (sampling noise, fresh every step)"] = lambda i: noise.normal_(generator=g)
-            if vn is not None and world > 1:
-                parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
-            parts["rollout_kernel<v2,policy>"] = lambda i: policy.forward(env.obs, noise, norm_stats=vn.stats if vn is not None else None)
-            parts["env_step_kernel<float,v2,rk4,moments>+moments_final"] = lambda i: env.step(policy.actions_clipped)
-    else:
-        u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
-
-        def regen(i):
-            u.uniform_(generator=g)
-            torch.addcmul(lo, u, span, out=a)
-        parts["torch uniform_ + addcmul (actions, fresh every step)"] = regen
-        parts[f"env_step_kernel<{'float' if args.precision == 'f32' else 'double'},v2,rk4>"] = lambda i: env.step(a)
+    parts = build_parts(args.rollout)
+    fused = fused_holder.get("f")
 
     def one_step(i):
         for fn in parts.values():
@@ -454,6 +469,16 @@ def run_gpu(args) -> None:
         if "xchg_merge_kernel" in parts:
             kernel_ms["xchg_merge_kernel (rendezvous: remainder of the step)"] = max(0.0, ms_step - sum(kernel_ms.values()))
     barrier()
+    # ---- the same rollout workload through the OTHER launch structure (one fused kernel vs policy kernel + step kernel), same process
+    pre_extras = []
+    if args.workload == "rollout" and world == 1 and not args.no_extras:
+        other = "separate" if args.rollout == "fused" else "fused"
+        oparts = build_parts(other)
+        oms, og = graph_time(lambda i: [fn(i) for fn in oparts.values()], 200, 4, dev)
+        del og
+        pre_extras.append({"workload": workload_name(args), "rollout": other, "value": n / (oms / 1e3), "unit": UNIT, "ms_per_step": oms,
+                           "dtype": args.precision, "kernels": list(oparts),
+                           "note": "same workload, the other launch structure (default is the faster one)"})
 
     # ---- end to end through the SB3-style VecEnv call: pinned host actions in, obs/reward/done out --------
     from rl_aerial_manipulator_b200.vec_env import QuadVecEnv
@@ -525,6 +550,7 @@ def run_gpu(args) -> None:
         extras = []
         if world == 1 and not args.no_extras:
             # the other single-GPU configurations of BASELINE.json (configs[2] and the float64 modes), short runs in the same process
+            extras.extend(pre_extras)
             for (en, prec, integ, st) in ((1 << 20, "f32", "rk4", 200), (1 << 20, "f64", "rk4", 100), (65536, "f32", "rk4", 400),
                                          (65536, "f64", "rk4", 400), (65536, "f64", "lsoda", 6)):
                 if args.workload == "step" and en == n and prec == args.precision and integ == "rk4":
@@ -581,7 +607,7 @@ def main():
     ap.add_argument("--vecnorm-exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: how ranks exchange the VecNormalize moments (peer = fused all-gather+merge kernel over NVLink peer memory)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step loop from a CUDA graph (4 steps per graph)")
-    ap.add_argument("--rollout", default="fused", choices=["fused", "separate"],
+    ap.add_argument("--rollout", default="separate", choices=["fused", "separate"],
                     help="rollout workload: one fused kernel per step (in-kernel Philox noise), or policy kernel + env-step kernel + torch normal_")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra single-GPU workload lines (configs[2], float64, LSODA)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -149,6 +149,36 @@ int qs_step_range(qs_handle* h, int64_t first_env, int64_t count, const float* a
                   uint8_t* flags_out, float* terminal_obs_out, void* ep_return_out, int32_t* ep_len_out, void* stream);
 
 /*
+ * T env steps in ONE launch: an env's hidden state stays in registers across the steps (throughput mode for small batches such
+ * as BASELINE.json configs[2], 65,536 envs, where a launch and a state round trip per step are the floor).  Same arithmetic as
+ * T calls of qs_step (the same device functions); RK4 handles only; not while qs_step_moments is armed.
+ *   T                steps per launch (>= 1)
+ *   actions          f32[T,n,4] time-major, or NULL: actions are drawn in the kernel, uniform over [action_lo, action_hi) --
+ *                    Philox4x32-10 keyed on action_seed, counter = (global env id, *action_step + t); the last CTA to finish adds
+ *                    T to *action_step (device u64), so consecutive launches and CUDA-graph replays draw fresh actions
+ *   actions_out      f32[T,n,4] or NULL: the actions each step used (what a rollout buffer stores)
+ *   obs_out          f32[T,n,obs_dim] time-major (n * obs_dim must be a multiple of 4), or f32[n,obs_dim] = the observations after
+ *                    the last step when obs_last_only != 0
+ *   reward_out       [T,n] f32/f64; flags_out u8[T,n]; terminal_obs_out f32[T,n,obs_dim] / ep_return_out [T,n] / ep_len_out i32[T,n]
+ *                    or NULL, rows written where the env finished in that step
+ */
+typedef struct qs_step_many_args {
+    int32_t T, obs_last_only;
+    const float* actions;
+    uint64_t action_seed;
+    uint64_t* action_step;
+    float action_lo[4], action_hi[4];
+    float* actions_out;
+    float* obs_out;
+    void* reward_out;
+    uint8_t* flags_out;
+    float* terminal_obs_out;
+    void* ep_return_out;
+    int32_t* ep_len_out;
+} qs_step_many_args;
+int qs_step_many(qs_handle* h, const qs_step_many_args* a, void* stream);
+
+/*
  * Fused VecNormalize moments: after this call every qs_step also leaves (n, mean[D], M2[D]) of the observations it
  * returned (f64[1+2D], device, caller-owned) in `moments_out` -- what RunningMeanStd.update(obs) needs -- computed inside the
  * step kernel from the obs tile it already holds.  shift_stats: VecNormalize stats f64[1+2D] whose mean is used as the

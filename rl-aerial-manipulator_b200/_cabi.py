@@ -97,6 +97,14 @@ class QsRolloutArgs(C.Structure):
 SAMPLE_MEAN, SAMPLE_NOISE, SAMPLE_PHILOX = 0, 1, 2
 
 
+class QsStepManyArgs(C.Structure):
+    """qs_step_many_args of include/quadsim.h."""
+    _fields_ = [("T", C.c_int32), ("obs_last_only", C.c_int32), ("actions", C.c_void_p), ("action_seed", C.c_uint64),
+                ("action_step", C.c_void_p), ("action_lo", C.c_float * 4), ("action_hi", C.c_float * 4),
+                ("actions_out", C.c_void_p), ("obs_out", C.c_void_p), ("reward_out", C.c_void_p), ("flags_out", C.c_void_p),
+                ("terminal_obs_out", C.c_void_p), ("ep_return_out", C.c_void_p), ("ep_len_out", C.c_void_p)]
+
+
 class QsPpoHyper(C.Structure):
     """qs_ppo_hyper of include/quadsim.h."""
     _fields_ = [("clip_range", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float), ("max_grad_norm", C.c_float),
@@ -136,6 +144,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.qs_step.argtypes = [vp] + [vp] * 7 + [vp]
     lib.qs_step_range.argtypes = [vp, i64, i64] + [vp] * 7 + [vp]
     lib.qs_step_range.restype = C.c_int
+    lib.qs_step_many.argtypes = [vp, C.POINTER(QsStepManyArgs), vp]
+    lib.qs_step_many.restype = C.c_int
     lib.qs_step_moments.argtypes = [vp, vp, vp]
     lib.qs_step_moments_merge.argtypes = [vp, vp]
     lib.qs_step_moments_merge.restype = C.c_int

@@ -131,6 +131,48 @@ class BatchedQuadEnv:
                                p(self.ep_return), p(self.ep_len), self._stream()), "qs_step")
         return StepOut(self.obs, self.reward, self.flags, self.terminal_obs, self.ep_return, self.ep_len)
 
+    def step_many(self, T: int, actions: torch.Tensor | None = None, action_seed: int = 0, store_actions: bool = False,
+                  obs_last_only: bool = False, store_terminal: bool = False, update_obs: bool = True) -> dict:
+        """T steps in ONE kernel launch (`qs_step_many`): the hidden state stays in registers across the steps.  `actions`
+        f32[T,n,4] time-major, or None: uniform-random actions over the action box drawn in the kernel (Philox on `action_seed`,
+        the global env id and a device-resident step counter, so repeated calls and CUDA-graph replays draw fresh actions).
+        Returns time-major device tensors {"obs": [T,n,D] (or [n,D] with obs_last_only), "reward": [T,n], "flags": [T,n], and
+        "actions" / "terminal_obs" / "ep_return" / "ep_len" when requested}; the buffers are reused by the next call with the
+        same T.  `self.obs` holds the observations after the last step (unless update_obs=False).  RK4 handles only."""
+        n, d, dev = self.n_envs, self.obs_dim, self.device
+        key = (int(T), bool(store_actions), bool(obs_last_only), bool(store_terminal))
+        buf = getattr(self, "_many", None)
+        if buf is None or buf["key"] != key:
+            buf = {"key": key, "obs": self.obs if obs_last_only else torch.empty((T, n, d), dtype=torch.float32, device=dev),
+                   "reward": torch.empty((T, n), dtype=self.real_dtype, device=dev), "flags": torch.zeros((T, n), dtype=torch.uint8, device=dev)}
+            if store_actions:
+                buf["actions"] = torch.empty((T, n, 4), dtype=torch.float32, device=dev)
+            if store_terminal:
+                buf["terminal_obs"] = torch.zeros((T, n, d), dtype=torch.float32, device=dev)
+                buf["ep_return"] = torch.zeros((T, n), dtype=self.real_dtype, device=dev)
+                buf["ep_len"] = torch.zeros((T, n), dtype=torch.int32, device=dev)
+            self._many = buf
+            if not hasattr(self, "_action_step"):
+                self._action_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        a = _cabi.QsStepManyArgs()
+        p = lambda t: t.data_ptr() if t is not None else None
+        a.T, a.obs_last_only = int(T), int(bool(obs_last_only))
+        if actions is not None:
+            if actions.dtype != torch.float32 or tuple(actions.shape) != (T, n, 4) or not actions.is_contiguous() or actions.device != dev:
+                raise ValueError(f"actions must be contiguous float32[{T},{n},4] on {dev}")
+            a.actions = p(actions)
+        a.action_seed = int(action_seed) & 0xFFFFFFFFFFFFFFFF
+        a.action_step = p(self._action_step)
+        a.action_lo[:] = (0.0, -1.0, -1.0, -1.0)          # the env's action box (rl_env_scaledObs.py:20-24)
+        a.action_hi[:] = (2.0, 1.0, 1.0, 1.0)
+        a.actions_out = p(buf.get("actions"))
+        a.obs_out, a.reward_out, a.flags_out = p(buf["obs"]), p(buf["reward"]), p(buf["flags"])
+        a.terminal_obs_out, a.ep_return_out, a.ep_len_out = p(buf.get("terminal_obs")), p(buf.get("ep_return")), p(buf.get("ep_len"))
+        check(self.lib, self._h, self.lib.qs_step_many(self._h, C.byref(a), self._stream()), "qs_step_many")
+        if not obs_last_only and update_obs:                  # keep `self.obs` = the observations after the last step (one D2D copy)
+            self.obs.copy_(buf["obs"][T - 1])
+        return {k: v for k, v in buf.items() if k != "key"}
+
     def step_range(self, first: int, count: int, actions: torch.Tensor, stream: torch.cuda.Stream | None = None) -> None:
         """Step envs [first, first + count) only (first a multiple of 32); `actions` is the f32[count,4] slice for them.  Results
         land in the same rows of the persistent output buffers.  Ordered on `stream` (default: the current stream) -- sub-ranges

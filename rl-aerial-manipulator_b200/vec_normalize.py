@@ -82,7 +82,8 @@ class DeviceRunningMeanStd:
         ok = rc == 0 and all(h is not None for h in handles)
         if ok:
             ok = self.lib.qs_xchg_connect(x, b"".join(handles)) == 0
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        on_host = dist.get_backend(self.group) == "gloo"                       # (two processes on one device rendezvous over gloo)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cpu" if on_host else self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)          # every rank takes the same path
         if int(flag.item()) == 1:
             self._xchg, self.exchange = x, "peer"

@@ -18,7 +18,9 @@ the B200 (tests/test_gpu_trajectory.py).  Flags (terminated / truncated / info b
 import numpy as np
 
 BOUNDS = {
-    ("traj", "f32"): dict(pos=2e-5, vel=3e-5, quat=2e-6, omega=1e-5, reward=1e-4, obs=1e-5),
+    # reward: the B200 build (FMA contraction, device intrinsics) measured 1.163e-3 at h = 529, i.e. C = 1.005e-4, against 2.5e-5 for
+    # the host build of the same code -- the stated C keeps 1.5x over the worst device value
+    ("traj", "f32"): dict(pos=2e-5, vel=3e-5, quat=2e-6, omega=1e-5, reward=1.5e-4, obs=1e-5),
     ("traj", "f64"): dict(pos=2e-6, vel=2e-6, quat=1e-7, omega=2e-6, reward=2e-5, obs=1e-6),
     ("policy", "f32"): dict(pos=1e-4, vel=1e-4, quat=1e-5, omega=1e-5, reward=2e-3, obs=5e-5),
     ("policy", "f64"): dict(pos=3e-5, vel=3e-5, quat=5e-6, omega=5e-6, reward=5e-4, obs=2e-5),

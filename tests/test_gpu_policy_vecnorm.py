@@ -223,6 +223,18 @@ def test_peer_memory_moment_exchange_matches_nccl_two_ranks():
 
 
 @pytest.mark.gpu
+def test_peer_memory_moment_exchange_two_processes_one_device():
+    """The same exchange kernel between two PROCESSES on one GPU (CUDA IPC works on the same device; NCCL does not, so the checker is
+    oracle/sb3_oracle.merge_moments and the rendezvous gloo): runs on a single-GPU box, where the two-rank test above is skipped."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", os.path.join(root, "tools", "peer_exchange_one_device.py")], cwd=root, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "PEER_ONE_DEVICE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.gpu
 def test_step_kernel_merges_running_statistics_itself():
     """attach(env, merge=True): RunningMeanStd.update happens inside qs_step (the kernel that finishes the moments); the running
     statistics must equal, bit for bit, those of the two-launch path (moments triplet -> qs_vecnorm_merge) on the same env."""

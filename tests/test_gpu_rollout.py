@@ -122,10 +122,14 @@ def test_fused_rollout_step_equals_separate_calls(golden_dir, n, env_version):
         # O(10) -- each build is within POLICY_TOL["tensor"] (1e-4 / 1e-2) of the float64 forward, so they are that close to each
         # other (measured: 7 of 16,396 means differ by more than 2e-5, the largest by 4.9e-5)
         torch.testing.assert_close(fused.actions, a_b, rtol=0, atol=POLICY_TOL["tensor"][0])
-        torch.testing.assert_close(fused.values, v_b, rtol=0, atol=2e-3)
+        torch.testing.assert_close(fused.values, v_b, rtol=0, atol=POLICY_TOL["tensor"][1])
         torch.testing.assert_close(fused.actions_clipped, ac_b, rtol=0, atol=POLICY_TOL["tensor"][0])
-        assert float((fused.actions - a_b).abs().mean()) < 2e-6
-        assert torch.equal(fused.logp, lp_b) and torch.equal(fused.obs_norm, obs_norm_b), f"t={t}"
+        assert float((fused.actions - a_b).abs().mean()) < 2e-6 and float((fused.values - v_b).abs().mean()) < 5e-4
+        # the log-prob depends on the noise alone; the normalised observations on the running statistics, which the two paths
+        # finish with different partial sums (last-CTA reduction vs moments_final_kernel): equal to 1e-9 relative, so a float32
+        # normalised observation may differ in its last bit
+        assert torch.equal(fused.logp, lp_b), f"t={t}"
+        torch.testing.assert_close(fused.obs_norm, obs_norm_b, rtol=1e-6, atol=2e-6)
         same = out_a.flags == out_b.flags
         assert (~same).sum() <= max(1, n // 2000), f"t={t}: {(~same).sum()} flag mismatches"
         if not bool(same.all()):               # an env straddling a threshold by a float32 ulp diverges from here on: re-align it

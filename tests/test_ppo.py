@@ -248,3 +248,17 @@ def test_ppo_two_ranks_stay_in_lockstep():
                         "--master-port", "29523", os.path.join(root, "tools", "ppo_multi_rank_check.py")], cwd=root, capture_output=True,
                        text=True, timeout=400)
     assert r.returncode == 0 and "PPO_MULTI_RANK_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.gpu
+def test_ppo_two_processes_one_device_stay_in_lockstep():
+    """The same check with both ranks on ONE GPU (gloo rendezvous; the moment exchange still runs over CUDA IPC peer memory, the
+    gradient all-reduce through gloo): sharded envs + qs_ppo_grad / all-reduce / qs_ppo_apply keep parameters and statistics
+    bit-identical on both ranks.  Runs on the single-GPU box where the two-GPU test is skipped."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QS_ONE_DEVICE="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "ppo_multi_rank_check.py")], cwd=root, capture_output=True,
+                       text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "PPO_MULTI_RANK_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

@@ -372,11 +372,11 @@ def run_gpu(args) -> None:
                 if vn is not None and world > 1:
                     parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
             else:
-                noise = torch.empty((n, 4), device=dev)
-                parts["torch normal_ (sampling noise, fresh every step)"] = lambda i: noise.normal_()
+                # two kernels per step: tcgen05 pipeline policy kernel (normalise, forward, in-kernel Philox sampling, clip) + env step
                 if vn is not None and world > 1:
                     parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
-                parts["rollout_kernel<v2,policy>"] = lambda i: policy.forward(env.obs, noise, norm_stats=vn.stats if vn is not None else None)
+                parts["rollout_kernel<v2,policy>"] = lambda i: policy.forward_sampled(env.obs, noise_seed=args.seed, env_id_offset=rank * n,
+                                                                                     norm_stats=vn.stats if vn is not None else None)
                 parts["env_step_kernel<float,v2,rk4,moments>+moments_final"] = lambda i: env.step(policy.actions_clipped)
         else:
             u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
@@ -572,7 +572,7 @@ def run_gpu(args) -> None:
                            "vecnormalize": bool(vn is not None), "cuda_graph": bool(unroll),
                            "rollout": (args.rollout if args.workload == "rollout" else None),
                            "actions": ("policy (ppo_model_2300000_steps weights), Gaussian noise drawn every step "
-                                       + ("inside the kernel (Philox4x32-10 on seed, global env id, step + Box-Muller)" if fused is not None else "by torch normal_ inside the timed region")
+                                       + "inside the kernel (Philox4x32-10 on seed, global env id, step + Box-Muller)"
                                        + ", clipped to the action box") if policy else "uniform-random over the action box, regenerated on the device every step inside the timed region",
                            "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
                            "parallelism": f"env-shard x{world}, no data-path collective",

@@ -250,13 +250,22 @@ const char* qs_vecnorm_last_error(void);
 #define QS_POLICY_TENSOR_PIPELINE 4 /* QS_POLICY_TENSOR arithmetic on the warp-specialised pipeline of qs_rollout_step (policy part only) */
 #define QS_POLICY_TENSOR_CHAINS 5   /* QS_POLICY_TENSOR arithmetic on the three-chain kernel (qs_policy_tc.cu) */
 #ifndef QS_POLICY_TENSOR_DEFAULT_PIPELINE
-#define QS_POLICY_TENSOR_DEFAULT_PIPELINE 0 /* which of the two QS_POLICY_TENSOR / AUTO run */
+#define QS_POLICY_TENSOR_DEFAULT_PIPELINE 1 /* which of the two QS_POLICY_TENSOR / AUTO run (r02: pipeline 296 us, chains 308 us per 1M envs) */
 #endif
 int64_t qs_policy_param_count(int obs_dim);
 int qs_policy_forward(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n,
                       const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out,
                       float* actions, float* actions_clipped, const float* clip_lo, const float* clip_hi,
                       float* values, float* logp, int impl, void* stream);
+/* The same forward with the sampling noise drawn INSIDE the kernel (what SB3's DiagGaussianDistribution.sample does every rollout
+ * step, call site initial-implementation-v2/rl_train.py:27): Philox4x32-10 keyed on noise_seed, counter = (env_id_offset + row,
+ * step) + Box-Muller, the generator of qs_rollout_step's QS_SAMPLE_PHILOX.  counter: device u64[2], 16-byte aligned, zeroed by
+ * the caller once -- [0] is the step index (the last CTA to finish adds 1, so consecutive launches and CUDA-graph replays draw
+ * fresh noise), [1] is scratch.  Runs on the tcgen05 pipeline kernel (QS_POLICY_TENSOR_PIPELINE arithmetic). */
+int qs_policy_forward_philox(const float* params, int obs_dim, const float* obs, int64_t n, uint64_t noise_seed, uint64_t* counter,
+                             int64_t env_id_offset, const double* norm_stats, float norm_eps, float norm_clip,
+                             float* obs_norm_out, float* actions, float* actions_clipped, const float* clip_lo,
+                             const float* clip_hi, float* values, float* logp, void* stream);
 const char* qs_policy_last_error(void);
 
 /* Fused rollout step -----------------------------------------------------------------------------------

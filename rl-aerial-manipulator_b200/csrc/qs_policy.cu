@@ -234,7 +234,7 @@ int launch_policy_tc(int precise, const float* params, int obs_dim, const float*
 int launch_policy_pipeline(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n, const double* norm_stats,
                            float norm_eps, float norm_clip, float* obs_norm_out, float* actions, float* actions_clipped,
                            const float* clip_lo, const float* clip_hi, float* values, float* logp, cudaStream_t stream,
-                           const char** err_out);
+                           const char** err_out, uint64_t philox_seed = 0, uint64_t* philox_counter = nullptr, int64_t env_id_offset = 0);
 
 }  // namespace qs
 
@@ -307,6 +307,28 @@ int qs_policy_forward(const float* params, int obs_dim, const float* obs, const 
         return QS_ECUDA;
     }
     return QS_OK;
+}
+
+/* qs_policy_forward with the Gaussian noise drawn inside the kernel (tcgen05 pipeline kernel only). */
+int qs_policy_forward_philox(const float* params, int obs_dim, const float* obs, int64_t n, uint64_t noise_seed, uint64_t* counter,
+                             int64_t env_id_offset, const double* norm_stats, float norm_eps, float norm_clip, float* obs_norm_out,
+                             float* actions, float* actions_clipped, const float* clip_lo, const float* clip_hi, float* values,
+                             float* logp, void* stream) {
+    if (!params || !obs || !actions || !values || !logp || !counter || n < 0 || (obs_dim != 17 && obs_dim != 20)) {
+        snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward_philox: bad argument (obs_dim 17 or 20; counter = device u64[2])");
+        return QS_EINVAL;
+    }
+    if (n == 0) return QS_OK;
+    if ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(actions_clipped) |
+         reinterpret_cast<uintptr_t>(obs_norm_out) | reinterpret_cast<uintptr_t>(counter)) & 15) {
+        snprintf(g_policy_error, sizeof(g_policy_error), "qs_policy_forward_philox: obs, actions, actions_clipped, obs_norm_out and counter must be 16-byte aligned");
+        return QS_EINVAL;
+    }
+    const char* msg = nullptr;
+    const int rc = launch_policy_pipeline(params, obs_dim, obs, nullptr, n, norm_stats, norm_eps, norm_clip, obs_norm_out, actions, actions_clipped,
+                                          clip_lo, clip_hi, values, logp, (cudaStream_t)stream, &msg, noise_seed, counter, env_id_offset);
+    if (rc != QS_OK && msg) snprintf(g_policy_error, sizeof(g_policy_error), "%s", msg);
+    return rc;
 }
 
 }  // extern "C"

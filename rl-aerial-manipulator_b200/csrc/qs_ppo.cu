@@ -317,15 +317,27 @@ __device__ __forceinline__ void adam_apply(const Args& a, const float* __restric
     const long long t = *a.step + 1;
     const double bc1 = 1.0 - pow((double)a.hp.beta1, (double)t), bc2 = 1.0 - pow((double)a.hp.beta2, (double)t);
     const float step_size = (float)((double)a.hp.lr / bc1), rsq_bc2 = (float)(1.0 / sqrt(bc2));
-    for (int p = threadIdx.x; p < a.n_params; p += THREADS) {
-        const float gp = g[p] * coef;
-        float m = a.m[p], v = a.v[p];
-        m = m + (gp - m) * (1.0f - a.hp.beta1);                    // exp_avg.lerp_(grad, 1 - beta1)
-        v = v * a.hp.beta2 + (1.0f - a.hp.beta2) * gp * gp;        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        a.m[p] = m;
-        a.v[p] = v;
-        const float denom = sqrtf(v) * rsq_bc2 + a.hp.adam_eps;
-        a.params[p] = a.params[p] - step_size * (m / denom);
+    // four parameters per thread and pass: their m / v / parameter loads are all in flight together (one CTA does this alone)
+    for (int p0 = threadIdx.x; p0 < a.n_params; p0 += 4 * THREADS) {
+        float m[4], v[4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * THREADS;
+            const bool ok = p < a.n_params;
+            m[u] = ok ? a.m[p] : 0.f; v[u] = ok ? a.v[p] : 0.f; w[u] = ok ? a.params[p] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * THREADS;
+            if (p >= a.n_params) continue;
+            const float gp = g[p] * coef;
+            const float mu = m[u] + (gp - m[u]) * (1.0f - a.hp.beta1);                    // exp_avg.lerp_(grad, 1 - beta1)
+            const float vu = v[u] * a.hp.beta2 + (1.0f - a.hp.beta2) * gp * gp;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+            a.m[p] = mu;
+            a.v[p] = vu;
+            const float denom = sqrtf(vu) * rsq_bc2 + a.hp.adam_eps;
+            a.params[p] = w[u] - step_size * (mu / denom);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) *a.step = t;
@@ -475,14 +487,27 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_update_kernel(const Args a) {
     float* g = reinterpret_cast<float*>(smem_raw);                // n_params floats <= sizeof(Smem) (checked on the host)
     double nsq = 0.0;
     __syncthreads();
-    for (int p = tid; p < a.n_params; p += THREADS) {
-        float acc = 0.f;
-        for (unsigned c = 0; c < gridDim.x; ++c) acc += __ldcg(a.partial + (size_t)c * a.n_params + p);
-        // the entropy bonus: d(-ent_coef * mean(entropy))/d log_std = -ent_coef
-        if (p >= B.log_std()) acc -= a.hp.ent_coef;
-        g[p] = acc;
-        nsq += (double)acc * (double)acc;
-        if (a.grad_out) a.grad_out[p] = acc;
+    for (int p0 = tid; p0 < a.n_params; p0 += 4 * THREADS) {          // four parameters per thread and pass: 4 x grid loads in flight
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (unsigned c = 0; c < gridDim.x; ++c) {                    // slabs in CTA order: the sum is deterministic
+            const float* slab_c = a.partial + (size_t)c * a.n_params;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int p = p0 + u * THREADS;
+                if (p < a.n_params) acc[u] += __ldcg(slab_c + p);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * THREADS;
+            if (p >= a.n_params) continue;
+            // the entropy bonus: d(-ent_coef * mean(entropy))/d log_std = -ent_coef
+            if (p >= B.log_std()) acc[u] -= a.hp.ent_coef;
+            g[p] = acc[u];
+            nsq += (double)acc[u] * (double)acc[u];
+            if (a.grad_out) a.grad_out[p] = acc[u];
+        }
     }
     __shared__ double red2[40];
     nsq = block_sum(nsq, red2);

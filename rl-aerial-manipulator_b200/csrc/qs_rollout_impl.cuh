@@ -810,7 +810,20 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_kernel(const RoParams p
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(TMEM_COLS));
     }
-    if (!FUSED) return;
+    if (!FUSED) {
+        // in-kernel sampling without the env step: the last CTA to finish advances the device step counter (ticket = counter[1])
+        if (p.sample_mode == 2 && p.noise_step) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_misc[1] = atomicAdd(p.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+            __syncthreads();
+            if (s_misc[1] != 0u && tid == 0) {
+                *p.ticket = 0u;
+                *p.noise_step = noise_step + 1ull;
+            }
+        }
+        return;
+    }
 
     // ---- per-CTA moment partials, then the LAST CTA to finish: fixed-order sum of the partials -> (n, mean, M2) -> Chan merge
     const StepParams<float>& sp = p.sp;
@@ -911,12 +924,18 @@ static cudaError_t launch(const RoParams& p, int sms, cudaStream_t st) {
 int launch_policy_pipeline(const float* params, int obs_dim, const float* obs, const float* noise, int64_t n, const double* norm_stats,
                            float norm_eps, float norm_clip, float* obs_norm_out, float* actions, float* actions_clipped,
                            const float* clip_lo, const float* clip_hi, float* values, float* logp, cudaStream_t stream,
-                           const char** err_out) {
+                           const char** err_out, uint64_t philox_seed, uint64_t* philox_counter, int64_t env_id_offset) {
     static thread_local char msg[256];
     QS_RO_NS::RoParams p;
     memset(&p, 0, sizeof(p));
     p.params = params; p.obs = obs; p.norm = norm_stats; p.norm_eps = norm_eps; p.norm_clip = norm_clip;
     p.sample_mode = noise ? 1 : 0; p.noise = noise;
+    if (philox_counter) {             // in-kernel Gaussian noise: counter[0] = step (advanced by the kernel), counter[1] = last-CTA ticket
+        p.sample_mode = 2; p.noise = nullptr; p.noise_seed = philox_seed;
+        p.noise_step = reinterpret_cast<unsigned long long*>(philox_counter);
+        p.ticket = reinterpret_cast<unsigned int*>(philox_counter + 1);
+        p.sp.env_id_offset = env_id_offset;
+    }
     for (int i = 0; i < 4; ++i) { p.lo[i] = clip_lo ? clip_lo[i] : -3.4e38f; p.hi[i] = clip_hi ? clip_hi[i] : 3.4e38f; }
     p.obs_norm_out = obs_norm_out; p.actions = actions; p.actions_clipped = actions_clipped; p.values = values; p.logp = logp; p.n = n;
     int dev = 0, sms = 0;

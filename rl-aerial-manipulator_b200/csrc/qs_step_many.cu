@@ -54,8 +54,14 @@ __device__ __forceinline__ float4 philox_uniform_action(uint64_t seed, uint64_t 
     return a;
 }
 
+// Resident CTAs per SM the kernel is compiled for.  The mode exists for SMALL batches: at 65,536 envs there are 13.8 warps per SM, so
+// the float32 kernel is held to 128 registers (4 CTAs = 16 warps per SM: every env resident in one wave, no second round of T
+// steps for a leftover third of the warps); float64 needs the registers more (3 CTAs, 168 registers).
+template <typename Real> struct ManyOcc { static constexpr int MINB = 3; };
+template <> struct ManyOcc<float> { static constexpr int MINB = 4; };
+
 template <typename Real, int VER>
-__global__ void __launch_bounds__(STEP_BLOCK, 2) env_step_many_kernel(const ManyParams<Real> p) {
+__global__ void __launch_bounds__(STEP_BLOCK, ManyOcc<Real>::MINB) env_step_many_kernel(const ManyParams<Real> p) {
     constexpr int OBS = EnvTraits<VER>::OBS;
     __shared__ float s_tile[STEP_BLOCK / 32][32 * (OBS + 1)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

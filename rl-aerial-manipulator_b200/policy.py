@@ -34,6 +34,9 @@ def _bind(lib):
     lib.qs_policy_forward.argtypes = [vp, C.c_int, vp, vp, C.c_int64, vp, f32, f32, vp, vp, vp,
                                       C.POINTER(f32 * 4), C.POINTER(f32 * 4), vp, vp, C.c_int, vp]
     lib.qs_policy_forward.restype = C.c_int
+    lib.qs_policy_forward_philox.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_uint64, vp, C.c_int64, vp, f32, f32, vp, vp, vp,
+                                             C.POINTER(f32 * 4), C.POINTER(f32 * 4), vp, vp, vp]
+    lib.qs_policy_forward_philox.restype = C.c_int
     lib.qs_policy_last_error.restype = C.c_char_p
     lib._policy_bound = True
 
@@ -147,6 +150,25 @@ class MlpPolicyKernel:
                                         C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"qs_policy_forward failed ({rc}): {self.lib.qs_policy_last_error().decode()}")
+        return self.actions, self.values, self.logp
+
+    def forward_sampled(self, obs: torch.Tensor, noise_seed: int = 0, env_id_offset: int = 0, norm_stats: torch.Tensor | None = None,
+                        norm_eps: float = 1e-8, norm_clip: float = 10.0, obs_norm_out: torch.Tensor | None = None):
+        """forward() with the Gaussian noise drawn inside the kernel (`qs_policy_forward_philox`: Philox on the seed, the GLOBAL env
+        id and a device-resident step counter -- fresh noise on every call and every CUDA-graph replay, shard independent).  Runs on
+        the tcgen05 pipeline kernel whatever `impl` says.  Returns (actions, values, logp); `actions_clipped` as in forward()."""
+        n = obs.shape[0]
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape[1] == self.obs_dim and obs.device == self.device
+        self._ensure(n)
+        if getattr(self, "_philox_counter", None) is None:
+            self._philox_counter = torch.zeros(2, dtype=torch.int64, device=self.device)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = self.lib.qs_policy_forward_philox(p(self.params), self.obs_dim, p(obs), n, int(noise_seed) & 0xFFFFFFFFFFFFFFFF,
+                                               p(self._philox_counter), int(env_id_offset), p(norm_stats), norm_eps, norm_clip, p(obs_norm_out),
+                                               p(self.actions), p(self.actions_clipped), C.byref(self._lo), C.byref(self._hi), p(self.values),
+                                               p(self.logp), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"qs_policy_forward_philox failed ({rc}): {self.lib.qs_policy_last_error().decode()}")
         return self.actions, self.values, self.logp
 
     def _forward_range(self, first: int, count: int, obs, noise, norm_stats, stream) -> None:

@@ -231,7 +231,7 @@ def test_peer_memory_moment_exchange_two_processes_one_device():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29531", os.path.join(root, "tools", "peer_exchange_one_device.py")], cwd=root, capture_output=True,
                        text=True, timeout=300)
-    assert r.returncode == 0 and "PEER_ONE_DEVICE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "PEER_ONE_DEVICE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
 
 
 @pytest.mark.gpu

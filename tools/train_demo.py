@@ -15,4 +15,16 @@ def log(d):
     k[0] += 1
     if k[0] % max(1, iters // 25) == 0 or k[0] == 1:
         print(f"steps {d['timesteps']:.3e}  ep_rew_mean {d['ep_rew_mean']:9.2f} ({d['episodes']} eps)  loss {d['loss']:10.3f}  vf {d['value_loss']:10.3f}  t {time.time()-t0:6.1f}s", flush=True)
-ppo.learn(iters * n_steps * n, log=log)
+if os.environ.get("QS_PPO_BREAKDOWN"):
+    # wall-clock split of an iteration: rollout collection vs the minibatch updates (device-synchronised)
+    for it in range(iters):
+        torch.cuda.synchronize(); t1 = time.time()
+        ppo.collect_rollouts()
+        torch.cuda.synchronize(); t2 = time.time()
+        info = ppo.train()
+        torch.cuda.synchronize(); t3 = time.time()
+        nb = epochs * -(-n_steps * n // (batch or n * n_steps // 32))
+        print(f"iter {it}: collect {t2 - t1:.3f} s ({n_steps} steps), train {t3 - t2:.3f} s ({nb} minibatch updates = {1e6 * (t3 - t2) / nb:.1f} us each), "
+              f"loss {info['loss']:.3f} grad_norm {info['grad_norm']:.3f} clip_fraction {info['clip_fraction']:.3f}", flush=True)
+else:
+    ppo.learn(iters * n_steps * n, log=log)

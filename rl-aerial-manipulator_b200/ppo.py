@@ -193,6 +193,10 @@ class QuadPPO:
         self.advantages, self.returns = torch.empty((T, n), **f32), torch.empty((T, n), **f32)
         self.episode_starts = torch.zeros((T, n), dtype=torch.uint8, device=dev)
         self._noise = torch.empty((n, NACT), **f32)
+        self._boot_cap = min(n, max(256, n // 16))              # slots for time-limit bootstraps per step (overflow raises after the rollout)
+        self._boot_slots = torch.arange(self._boot_cap, device=dev)
+        self._boot_zero = torch.zeros((), **f32)
+        self._boot_overflow = torch.zeros((), dtype=torch.bool, device=dev)
         self._last_dones = torch.ones(n, dtype=torch.uint8, device=dev)
         self._last_obs = None
         self.num_timesteps = 0
@@ -234,11 +238,14 @@ class QuadPPO:
                 torch.clamp(out.reward / torch.sqrt(vn.ret_rms.var[0] + vn.epsilon), -vn.clip_reward, vn.clip_reward, out=self.rewards[t])
             else:
                 self.rewards[t].copy_(out.reward)
-            trunc_only = (out.flags & 3) == 2                        # TimeLimit.truncated: bootstrap with gamma * V(terminal_obs)
-            if bool(trunc_only.any()):                               # (one flag read per step; truncations are rare)
-                idx = trunc_only.nonzero(as_tuple=True)[0]
-                tv = self._forward(out.terminal_obs.index_select(0, idx).contiguous(), None, policy=self._aux)[1]
-                self.rewards[t].index_add_(0, idx, self.gamma * tv)
+            # TimeLimit.truncated: bootstrap with gamma * V(terminal_obs) -- without a host round trip: the truncated envs are compacted
+            # into a FIXED number of slots (nonzero_static; unused slots point at env 0 and add zero), so nothing waits for a count
+            trunc_only = (out.flags & 3) == 2
+            cnt = trunc_only.sum()
+            idx = torch.nonzero_static(trunc_only, size=self._boot_cap, fill_value=0)[:, 0]
+            tv = self._forward(out.terminal_obs.index_select(0, idx), None, policy=self._aux)[1]
+            self.rewards[t].index_add_(0, idx, torch.where(self._boot_slots < cnt, self.gamma * tv, self._boot_zero))
+            self._boot_overflow |= cnt > self._boot_cap
             done = (out.flags & 3) != 0
             self._last_dones = done.to(torch.uint8)
             self._ep_stats[0] += torch.where(done, out.ep_return.double(), self._zero).sum()     # Monitor-style episode returns,
@@ -249,6 +256,8 @@ class QuadPPO:
             out=(self.advantages, self.returns))
         if vn is not None and vn.norm_obs and vn.obs_rms.exchange_failed():
             raise RuntimeError("VecNormalize moment exchange timed out waiting for a rank: the running statistics are incomplete")
+        if bool(self._boot_overflow):
+            raise RuntimeError(f"more than {self._boot_cap} envs hit the time limit in one step: raise QuadPPO._boot_cap")
         self.num_timesteps += self.n_steps * env.n_envs * self.world
         s, c = self._ep_stats.tolist()
         self.ep_rew_mean = s / c if c > 0 else float("nan")     # mean return of the episodes that finished in this rollout

@@ -171,3 +171,35 @@ def test_info_dicts_follow_reference_and_sb3_conventions():
                         "terminal_observation": infos[5]["terminal_observation"], "episode": {"r": 12.345679, "l": 77, "t": 1.5}}
     np.testing.assert_array_equal(infos.done_indices, [2, 3, 4, 5])
     np.testing.assert_array_equal(infos[3]["terminal_observation"], np.arange(20, 40, dtype=np.float32))
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The binding's ctypes structures against include/quadsim.h as a C compiler lays them out (gcc, plain C: the header is the ABI
+    a maintainer of the reference binds): same size, same offset for every field."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from rl_aerial_manipulator_b200 import _cabi
+    structs = {"qs_config": _cabi.QsConfig, "qs_state_view": _cabi.QsStateView, "qs_rollout_args": _cabi.QsRolloutArgs,
+               "qs_step_many_args": _cabi.QsStepManyArgs, "qs_ppo_hyper": _cabi.QsPpoHyper, "qs_pid_gains": _cabi.QsPidGains}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "quadsim.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout
+    seen = 0
+    for ln in out.splitlines():
+        cname, field, val = ln.split()
+        cls = structs[cname]
+        want = C.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(val) == want, (cname, field, int(val), want)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())

@@ -296,8 +296,8 @@ def step_extra(n, precision, integrator, dev, seed, steps):
     lo = torch.tensor([0.0, -1, -1, -1], device=dev)
     span = torch.tensor([2.0, 2, 2, 2], device=dev)
     u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
-    many = integrator == "rk4" and n <= (1 << 18)         # small batches: T steps per launch (the launch is the floor there)
-    T = 16
+    many = integrator == "rk4"          # T steps per launch, actions drawn in the kernel (qs_step_many); LSODA: one launch per step
+    T = 16 if n <= (1 << 18) else 4     # small batches: the launch is the floor; 1M envs: 4 steps keep the [T, n, ...] record at 0.4 GB
     if many:
         # T steps per launch, state in registers, uniform actions drawn in the kernel (Philox on (seed, global env id, step))
         ms, graph = graph_time(lambda i: env.step_many(T, update_obs=False), max(1, steps // T), 1, dev)

@@ -59,6 +59,11 @@ constexpr int EPI_WARPS = 8 * EPI_SPLIT, ENV_WARPS = 4 * ENV_SPLIT, MMA_WARPS = 
 #ifndef QS_RO_LDBUF
 #define QS_RO_LDBUF 1
 #endif
+// QS_RO_LD_SPLIT: the epilogue loads a 32-column chunk as two 16-column halves and converts the first while the second is in
+// flight (tcgen05.ld latency off the warp's critical path); needs the k-step-local activation layout (see issue_chunk)
+#ifndef QS_RO_LD_SPLIT
+#define QS_RO_LD_SPLIT 0
+#endif
 constexpr int W_EPI0 = QS_RO_ENV_FIRST ? ENV_WARPS : 0, W_ENV0 = QS_RO_ENV_FIRST ? 0 : EPI_WARPS, W_MMA0 = EPI_WARPS + ENV_WARPS;
 // the block is padded to whole groups of 4 warps: registers are allocated per 4 warps anyway (a 448 x 144 launch is refused)
 constexpr int RO_WARPS = ((EPI_WARPS + ENV_WARPS + MMA_WARPS + 3) / 4) * 4;
@@ -200,7 +205,35 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok;
 }
+// QS_RO_TIGHT_WAIT (r02): the whole bounded wait is ONE asm block -- try_wait (hinted), branch, counter -- 5 SASS instructions per
+// wake-up instead of the ~16 the C loop compiled to.  A parked warp is woken by every barrier event of the CTA (measured: ~7.7M
+// wake-ups per 1M-env launch), and with the epilogue warps busy back to back those wake-ups competed for issue slots that were
+// 72 % taken (ncu): the loop's length is a cost, not a detail.  The bound stays: 2^22 wake-ups (seconds), then the sticky status.
+#ifndef QS_RO_TIGHT_WAIT
+#define QS_RO_TIGHT_WAIT 1
+#endif
 __device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int code) {
+#if QS_RO_TIGHT_WAIT
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "QS_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra QS_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 q, n, 4194304;\n\t"
+        "@q bra QS_WAIT_LOOP;\n\t"
+        "QS_WAIT_DONE:\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)(QS_RO_WAIT_HINT_NS > 0 ? QS_RO_WAIT_HINT_NS : 1000))
+        : "memory");
+    if (ok) return true;
+#else
     for (uint32_t it = 0; it < (1u << 17); ++it) {                 // x (up to) 20 us per try: seconds, not minutes
 #if QS_RO_BACKOFF_NS > 0
         __nanosleep(QS_RO_BACKOFF_NS);
@@ -208,6 +241,7 @@ __device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, in
         if (mbar_try(bar, parity)) return true;
         if ((it & 0xFF) == 0xFF && *reinterpret_cast<volatile int*>(&g_ro_status) != 0) break;   // somebody else already gave up
     }
+#endif
     atomicCAS(&g_ro_status, 0, code);
     return false;
 }
@@ -289,11 +323,13 @@ __device__ __forceinline__ void issue_chunk(uint32_t d, uint32_t a_col, int ch, 
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int ks = 2 * ch + j;
-        const uint32_t a_hi = a_col + 32u * ch + 8u * j;
+        // activation layout inside a 32-column chunk: QS_RO_LD_SPLIT = 0: [hi k-step 0 | hi k-step 1 | lo 0 | lo 1] (8 columns each);
+        // = 1: [hi 0 | lo 0 | hi 1 | lo 1], i.e. each k-step's 16 activations stay inside their own 16 columns
+        const uint32_t a_hi = a_col + 32u * ch + (QS_RO_LD_SPLIT ? 16u : 8u) * j;
         const uint64_t bh = make_desc(wh + ks * 2 * B_LBO, B_LBO, 128), bl = make_desc(wl + ks * 2 * B_LBO, B_LBO, 128);
         umma_ts(d, a_hi, bh, idesc, 1);
         umma_ts(d, a_hi, bl, idesc, 1);
-        umma_ts(d, a_hi + 16u, bh, idesc, 1);
+        umma_ts(d, a_hi + (QS_RO_LD_SPLIT ? 8u : 16u), bh, idesc, 1);
     }
 }
 
@@ -392,89 +428,139 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
 }
 // One 32-column accumulator chunk of this lane's row at `col`: tcgen05.ld -> tanh -> hi | lo split, stored in place over the chunk
 // (hi halves in columns [0,16), lo halves in [16,32)).  Eight activations at a time keep the live registers near 64.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+// eight activations of this lane's row: tanh -> hi | lo packed halves stored at hi_col / lo_col (4 columns each)
+__device__ __forceinline__ void tanh_split8(const uint32_t* v, uint32_t hi_col, uint32_t lo_col) {
+    float y[8];
+    tanh4_from_exponents(v, y);
+    tanh4_from_exponents(v + 4, y + 4);
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_h2_rn(y[2 * j], y[2 * j + 1], h[j], l[j]);
+    tmem_st4(hi_col, h);
+    tmem_st4(lo_col, l);
+}
 __device__ __forceinline__ void chunk_tanh_split(uint32_t col) {
     uint32_t v[32];
+#if QS_RO_LD_SPLIT
+    tmem_ld16(col, v);
+    tmem_ld_wait16(v);
+    tmem_ld16(col + 16u, v + 16);                     // in flight while the first 16 activations are converted (they stay inside columns [0, 16))
+    tanh_split8(v, col, col + 8u);
+    tanh_split8(v + 8, col + 4u, col + 12u);
+    tmem_ld_wait16(v + 16);
+    tanh_split8(v + 16, col + 16u, col + 24u);
+    tanh_split8(v + 24, col + 20u, col + 28u);
+#else
     tmem_ld32(col, v);
     tmem_ld_wait32(v);
 #pragma unroll
-    for (int sb = 0; sb < 4; ++sb) {
-        float y[8];
-        tanh4_from_exponents(v + 8 * sb, y);
-        tanh4_from_exponents(v + 8 * sb + 4, y + 4);
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split_h2_rn(y[2 * j], y[2 * j + 1], h[j], l[j]);
-        tmem_st4(col + 4u * sb, h);
-        tmem_st4(col + 16u + 4u * sb, l);
-    }
+    for (int sb = 0; sb < 4; ++sb) tanh_split8(v + 8 * sb, col + 4u * sb, col + 16u + 4u * sb);
+#endif
 }
 
+// Order of a warp's work (QS_RO_DEFER_HEAD, r02): the head of job j-1 runs BETWEEN the layer-1 and the layer-2 epilogue of job j,
+//     E1(j) -> head(j-1) -> E2(j) -> E1(j+1) -> head(j) -> E2(j+1) -> ...
+// instead of E1(j) -> E2(j) -> head(j).  In the straight order the warp idles twice per job -- after E1 until the last two chunks'
+// MMAs have produced D2 (800-1,800 cycles) and after E2 until D3 (700-1,150; phase trace, profiles/r02) -- 40 % of a job.  Deferred,
+// every wait has a whole phase of other work in front of it: D3(j-1) has had E1(j) to complete, D2(j) completes under head(j-1), and
+// D1(j+1) (issued behind layer 2 of job j) under head(j-1) + E2(j).  Nothing else changes: D3 is not overwritten before layer 3 of
+// job j, which the MMA warp issues after E2(j) and after D3FREE, i.e. after head(j-1).  The env warps consume a tile's outputs one
+// iteration later to match (LAG in role_env).
+#ifndef QS_RO_DEFER_HEAD
+#define QS_RO_DEFER_HEAD 1
+#endif
 __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, int quad, int lane, const float* sC, float4* s_mean, float* s_val) {
     const uint32_t tm = c.tmem + slot * SLOT_COLS + ((uint32_t)(quad * 32) << 16);
     const int role = 100 + slot * 50;
     const int row = quad * 32 + lane;
-    uint32_t job = 0;
+    const uint32_t njobs = c.cnt > slot ? 2u * (uint32_t)((c.cnt - slot + 1) / 2) : 0u;    // two jobs (actor, critic) per tile of this slot
     float mean[NACT] = {0.f, 0.f, 0.f, 0.f};
     RO_TRACE_INIT();
-    for (int i = slot; i < c.cnt; i += 2) {
-        const uint32_t k = (uint32_t)i >> 1;
+    // iteration `job` does E1(job), head(job - DEFER), E2(job); one extra iteration drains the last head
 #pragma unroll 1
-        for (int net = 0; net < 2; ++net, ++job) {
-            const uint32_t par = job & 1u;
-            // chunks 0-3: layer-1 accumulator D1 -> H1; chunks 4-5: layer-2 accumulator D2 -> H2 (D2 follows D1 in the slot's columns);
-            // this warp takes every EPI_SPLIT-th chunk.  Each: tcgen05.ld -> tanh -> hi | lo in place -> signal the MMA warp.
+    for (uint32_t job = 0; job < njobs + QS_RO_DEFER_HEAD; ++job) {
+        const uint32_t par = job & 1u;
+        const bool live = job < njobs;
+        // chunks 0-3: layer-1 accumulator D1 -> H1; chunks 4-5: layer-2 accumulator D2 -> H2 (D2 follows D1 in the slot's columns);
+        // this warp takes every EPI_SPLIT-th chunk.  Each: tcgen05.ld -> tanh -> hi | lo in place -> signal the MMA warp.
 #pragma unroll 1
-            for (int ch = half; ch < 6; ch += EPI_SPLIT) {
-                if (ch == half && !mbar_wait_bounded(c.bar(B_D1 + slot), par, role + B_D1 + 1)) return;
-                if (ch == 4 + half && !mbar_wait_bounded(c.bar(B_D2 + slot), par, role + B_D2 + 1)) return;
-                if (ch == half || ch == 4 + half) tc_fence_after();
-                RO_TRACE(0x100000u | (ch << 12) | job);
-                chunk_tanh_split(tm + 32u * (uint32_t)ch);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(c.bar(ch < 4 ? B_H1 + slot * 4 + ch : B_H2 + slot * 2 + (ch - 4)));
-                RO_TRACE(0x110000u | (ch << 12) | job);
-            }
-            if (!mbar_wait_bounded(c.bar(B_D3 + slot), par, role + B_D3 + 1)) return;
-            RO_TRACE(0x130000u | job);
-            tc_fence_after();
-            float o[NACT];                                               // partial head sums of this warp's chunks (+ bias in half 0)
+        for (int stage = 0; stage < 3; ++stage) {
+            if (stage == (QS_RO_DEFER_HEAD ? 1 : 2)) {
+                // ---- head of job hj: layer-3 accumulator D3 -> tanh -> partial sums against the float32 head weights
+                if (QS_RO_DEFER_HEAD ? job == 0 : !live) continue;
+                const uint32_t hj = job - QS_RO_DEFER_HEAD, hpar = hj & 1u;
+                const int net = (int)(hj & 1u);
+                const uint32_t k = hj >> 1;                                  // this slot's tile counter
+                if (!mbar_wait_bounded(c.bar(B_D3 + slot), hpar, role + B_D3 + 1)) return;
+                RO_TRACE(0x130000u | hj);
+                tc_fence_after();
+                float o[NACT];                                               // partial head sums of this warp's chunks (+ bias in half 0)
 #pragma unroll
-            for (int j = 0; j < NACT; ++j) o[j] = half == 0 ? sC[C_BH + net * NACT + j] : 0.f;
+                for (int j = 0; j < NACT; ++j) o[j] = half == 0 ? sC[C_BH + net * NACT + j] : 0.f;
 #pragma unroll 1
-            for (int ch = half; ch < 2; ch += EPI_SPLIT) {
-                uint32_t v[32];
-                tmem_ld32(tm + C_D3 + 32u * (uint32_t)ch, v);
-                tmem_ld_wait32(v);
-                if (ch + EPI_SPLIT >= 2) {                               // this warp's last read of D3: layer 3 of the next job may overwrite it
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(c.bar(B_D3FREE + slot));
-                }
-                const float4* wh = reinterpret_cast<const float4*>(sC + C_WH + net * N3 * NACT) + 32 * ch;
+                for (int ch = half; ch < 2; ch += EPI_SPLIT) {
+                    uint32_t v[32];
+                    tmem_ld32(tm + C_D3 + 32u * (uint32_t)ch, v);
+                    tmem_ld_wait32(v);
+                    if (ch + EPI_SPLIT >= 2) {                               // this warp's last read of D3: layer 3 of the next job may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(c.bar(B_D3FREE + slot));
+                    }
+                    const float4* wh = reinterpret_cast<const float4*>(sC + C_WH + net * N3 * NACT) + 32 * ch;
 #pragma unroll
-                for (int sb = 0; sb < 4; ++sb) {
-                    float y[8];
-                    tanh4_from_exponents(v + 8 * sb, y);
-                    tanh4_from_exponents(v + 8 * sb + 4, y + 4);
+                    for (int sb = 0; sb < 4; ++sb) {
+                        float y[8];
+                        tanh4_from_exponents(v + 8 * sb, y);
+                        tanh4_from_exponents(v + 8 * sb + 4, y + 4);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 w = wh[8 * sb + q];
-                        o[0] = fmaf(y[q], w.x, o[0]); o[1] = fmaf(y[q], w.y, o[1]); o[2] = fmaf(y[q], w.z, o[2]); o[3] = fmaf(y[q], w.w, o[3]);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 w = wh[8 * sb + q];
+                            o[0] = fmaf(y[q], w.x, o[0]); o[1] = fmaf(y[q], w.y, o[1]); o[2] = fmaf(y[q], w.z, o[2]); o[3] = fmaf(y[q], w.w, o[3]);
+                        }
                     }
                 }
-            }
-            RO_TRACE(0x140000u | job);
-            if (net == 0) {
+                RO_TRACE(0x140000u | hj);
+                if (net == 0) {
 #pragma unroll
-                for (int j = 0; j < NACT; ++j) mean[j] = o[j];
+                    for (int j = 0; j < NACT; ++j) mean[j] = o[j];
+                } else {
+                    if (!mbar_wait_bounded(c.bar(B_OUTE + slot * 4 + quad), (k & 1u) ^ 1u, role + B_OUTE + 1)) return;
+                    s_mean[(slot * EPI_SPLIT + half) * ROWS + row] = make_float4(mean[0], mean[1], mean[2], mean[3]);
+                    s_val[(slot * EPI_SPLIT + half) * ROWS + row] = o[0];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(c.bar(B_OUTF + slot * 4 + quad));
+                }
             } else {
-                if (!mbar_wait_bounded(c.bar(B_OUTE + slot * 4 + quad), (k & 1u) ^ 1u, role + B_OUTE + 1)) return;
-                s_mean[(slot * EPI_SPLIT + half) * ROWS + row] = make_float4(mean[0], mean[1], mean[2], mean[3]);
-                s_val[(slot * EPI_SPLIT + half) * ROWS + row] = o[0];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(c.bar(B_OUTF + slot * 4 + quad));
+                // ---- E1 (first stage) or E2 of job `job`
+                if (!live) continue;
+                const bool first = stage == 0;
+                if (!mbar_wait_bounded(c.bar((first ? B_D1 : B_D2) + slot), par, role + (first ? B_D1 : B_D2) + 1)) return;
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = (first ? 0 : 4) + half; ch < (first ? 4 : 6); ch += EPI_SPLIT) {
+                    RO_TRACE(0x100000u | (ch << 12) | job);
+                    chunk_tanh_split(tm + 32u * (uint32_t)ch);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(c.bar(first ? B_H1 + slot * 4 + ch : B_H2 + slot * 2 + (ch - 4)));
+                    RO_TRACE(0x110000u | (ch << 12) | job);
+                }
             }
         }
     }
@@ -599,13 +685,18 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int pa
         if (par < c.cnt && e0 < p.n) pool_load<float, VER>(sp.pool, sp.n, e0, s_nx);
     }
     // the X tile of local tile i + 2 is staged before tile i is stepped; the first iteration(s) only stage (one call site: code size)
+    // With the deferred head (QS_RO_DEFER_HEAD) the outputs of a tile appear one job later, so this warp consumes them one of its
+    // iterations later too (LAG): staging the X tile of a later tile must not queue behind the wait for them (measured: every
+    // second job stalled ~4,000 cycles for its X tile otherwise).  The X buffers are released early (by the critic's layer-1 commit).
+    constexpr int LAG = QS_RO_DEFER_HEAD ? STRIDE : 0;
     RO_TRACE_INIT();
 #pragma unroll 1
-    for (int i = par - 2; i < c.cnt; i += STRIDE) {
-        RO_TRACE(0x300000u | (uint32_t)(i + 2));
-        if (i + 2 < c.cnt && !stage_x<OBS>(c, p, i + 2, quad, lane, smem, s_norm)) return;
-        RO_TRACE(0x310000u | (uint32_t)(i + 2));
-        if (i < 0) continue;
+    for (int j = par - 2; j < c.cnt + LAG; j += STRIDE) {
+        RO_TRACE(0x300000u | (uint32_t)(j + 2));
+        if (j + 2 < c.cnt && !stage_x<OBS>(c, p, j + 2, quad, lane, smem, s_norm)) return;
+        RO_TRACE(0x310000u | (uint32_t)(j + 2));
+        const int i = j - LAG;
+        if (i < 0 || i >= c.cnt) continue;
         const int slot = i & 1;
         const uint32_t k = (uint32_t)i >> 1;
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;

@@ -166,6 +166,13 @@ class QuadVecEnv(_SB3VecEnv):
         self.reset_infos = [{} for _ in range(self.num_envs)]
         return self._h_obs.numpy().copy()
 
+    @property
+    def pipelined(self) -> bool:
+        """True when step() goes through in chunks on separate streams (qs_step_range).  A device-side transform that needs the
+        WHOLE batch before it can produce any output row -- QuadVecNormalize updates the running statistics from all observations
+        of the step and only then normalises them -- switches the host pipeline off: one launch, one upload, one download."""
+        return len(self._chunks) > 1 and self._transform is None
+
     def step_async(self, actions: np.ndarray) -> None:
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
         src = torch.from_numpy(a)
@@ -174,7 +181,7 @@ class QuadVecEnv(_SB3VecEnv):
             src = self._h_actions
         self._flip ^= 1
         self._h_obs, self._h_reward, self._h_flags = self._h_bufs[self._flip]
-        if len(self._chunks) > 1 and self._transform is None:
+        if self.pipelined:
             sim = self.sim
             for (f, c), st in zip(self._chunks, self._chunk_streams):
                 sl = slice(f, f + c)
@@ -197,7 +204,7 @@ class QuadVecEnv(_SB3VecEnv):
 
     def step_wait(self):
         assert self._pending, "step_wait() without step_async()"
-        if len(self._chunks) > 1 and self._transform is None:
+        if self.pipelined:
             for st in self._chunk_streams:
                 st.synchronize()
         self._stream.synchronize()

@@ -175,7 +175,15 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     h->mom_merge = nullptr;
     h->range_first = 0;
     h->range_count = 0;
+    // last-CTA election counter of qs_rollout_step / qs_step_many: allocated here, not lazily, so that the first call of either may
+    // already be inside a CUDA-graph capture (cudaMemset on the legacy stream is illegal there)
     h->ro_ticket = nullptr;
+    if (cudaMalloc(&h->ro_ticket, sizeof(unsigned int)) != cudaSuccess || cudaMemset(h->ro_ticket, 0, sizeof(unsigned int)) != cudaSuccess) {
+        set_error(nullptr, "qs_create: ticket allocation failed");
+        cudaFree(h->pool);
+        delete h;
+        return QS_ENOMEM;
+    }
     h->ls_tables = nullptr;
     h->ls_counters = nullptr;
     h->ls_steps = nullptr;

@@ -171,7 +171,7 @@ class QuadPPO:
     def __init__(self, env, vecnorm=None, state_dict: dict | None = None, n_steps: int = 64, batch_size: int = 65536, n_epochs: int = 10,
                  gamma: float = 0.995, gae_lambda: float = 0.9, clip_range: float = 0.2, ent_coef: float = 0.01, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 2e-4, normalize_advantage: bool = True, seed: int = 0,
-                 policy_impl: str = "auto"):
+                 policy_impl: str = "auto", boot_cap: int | None = None):
         self.env, self.vecnorm = env, vecnorm
         self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
         self.gamma, self.gae_lambda = gamma, gae_lambda
@@ -193,7 +193,9 @@ class QuadPPO:
         self.advantages, self.returns = torch.empty((T, n), **f32), torch.empty((T, n), **f32)
         self.episode_starts = torch.zeros((T, n), dtype=torch.uint8, device=dev)
         self._noise = torch.empty((n, NACT), **f32)
-        self._boot_cap = min(n, max(256, n // 16))              # slots for time-limit bootstraps per step (overflow raises after the rollout)
+        # slots for time-limit bootstraps per step: every env up to 65,536 envs (no overflow possible), a sixteenth of the shard above
+        # that (more than 6 % of a shard hitting the limit in the same step raises after the rollout; `boot_cap` overrides)
+        self._boot_cap = int(boot_cap) if boot_cap else (n if n <= 65536 else max(65536, n // 16))
         self._boot_slots = torch.arange(self._boot_cap, device=dev)
         self._boot_zero = torch.zeros((), **f32)
         self._boot_overflow = torch.zeros((), dtype=torch.bool, device=dev)

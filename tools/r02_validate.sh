@@ -1,6 +1,7 @@
 #!/bin/bash
+# round-2 validation on one B200 (run through gpurun): smoke(), the full GPU suite, the default bench line, the reference arm
 set -u
-OUT=gpurun_out/r02m
+OUT=gpurun_out/r02_validate
 mkdir -p $OUT
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke.log | cut -c1-100
 timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "rc=$?" >> $OUT/pytest_gpu.log; tail -4 $OUT/pytest_gpu.log

@@ -1,5 +1,6 @@
 """On-device PPO run (tools, not a test): prints ep_rew_mean per iteration.
-python tools/train_demo.py [n_envs] [iters] [n_steps] [batch] [epochs] [env_version]"""
+python tools/train_demo.py [n_envs] [iters] [n_steps] [batch] [epochs] [env_version]      (QS_PPO_ENT=<ent_coef>, default 0.01)
+reference settings: v1/rl_train_vecN.py: 8 .. 2048 128 10 1 (ent 0.01); v2/rl_train.py: 8 .. 2048 128 12 2 with QS_PPO_ENT=0.0005"""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import torch
@@ -8,7 +9,7 @@ from rl_aerial_manipulator_b200.ppo import QuadPPO
 arg = lambda i, d: int(sys.argv[i]) if len(sys.argv) > i else d
 n, iters, n_steps, batch, epochs, ver = arg(1, 16384), arg(2, 30), arg(3, 128), arg(4, 0), arg(5, 4), arg(6, 2)
 env = BatchedQuadEnv(n, env_version=ver, precision="f32", seed=0)
-ppo = QuadPPO(env, n_steps=n_steps, batch_size=batch or n * n_steps // 32, n_epochs=epochs, learning_rate=2e-4, ent_coef=0.01, seed=0)
+ppo = QuadPPO(env, n_steps=n_steps, batch_size=batch or n * n_steps // 32, n_epochs=epochs, learning_rate=2e-4, ent_coef=float(os.environ.get("QS_PPO_ENT", "0.01")), seed=0)
 t0 = time.time()
 k = [0]
 def log(d):

@@ -263,6 +263,10 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
 // LOP3 / FADD / 2 x F2FP sequence of qs_tc.cuh::split_h2 costs 6)
 __device__ __forceinline__ void split_h2_rn(float a, float b, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+#ifdef QS_X_NOSPLIT                          // timing experiment only (wrong numerics): what the lo half costs
+    lo = hi ^ 0x3C003C00u;
+    return;
+#endif
     float la, lb;
     asm("{\n\t"
         ".reg .f16 l, h, m;\n\t"

@@ -139,8 +139,54 @@ __device__ __forceinline__ float tanh_from_exponent(float u) {
 #ifndef QS_TC_RCP_SHARE
 #define QS_TC_RCP_SHARE 4
 #endif
+// 2^u on the FMA pipe (Cody-Waite: n = round(u) by the 1.5 * 2^23 trick, degree-5 minimax of 2^f on [-0.5, 0.5], exponent added as an
+// integer).  u is clamped to [-126, 126].  Experimental (QS_X_POLY = how many of every four exponentials take this route).
+__device__ __forceinline__ float ex2_poly(float u) {
+    u = fminf(fmaxf(u, -126.0f), 126.0f);
+    const float magic = 12582912.0f;                       // 1.5 * 2^23
+    const float nf = u + magic;
+    const float f = u - (nf - magic);
+    float pz = 1.3333558146e-3f;
+    pz = fmaf(pz, f, 9.6181291076e-3f);
+    pz = fmaf(pz, f, 5.5504108665e-2f);
+    pz = fmaf(pz, f, 2.4022650696e-1f);
+    pz = fmaf(pz, f, 6.9314718056e-1f);
+    pz = fmaf(pz, f, 1.0f);
+    return __int_as_float(__float_as_int(pz) + (__float_as_int(nf) << 23));
+}
+// QS_TC_TANH_SAT (r02): the clamp, the +1 and a power-of-two scale in ONE instruction: a_i' = sat(2^u_i * s + s) = min(2^u_i + 1, 2^31) * s
+// with s = 2^-31 (FFMA.SAT; exact scaling, the same rounding as the add), so a_i' lies in [2^-31, 1], the product of four in
+// [2^-124, 1] (no overflow, no flush), and beyond 2^u + 1 = 2^31 tanh is 1.0f to the last bit anyway.  The scale comes back with
+// the -2 of tanh = 1 - 2/a: 1/a_i = s / a_i'.  19 instructions per four activations instead of 23 (MIN and FADD gone).
+// A NaN exponent leaves the group non-finite (sat flushes NaN to 0 -> 1/0), which the next layer's MMAs spread over the row.
+#ifndef QS_TC_TANH_SAT
+#define QS_TC_TANH_SAT 1
+#endif
 __device__ __forceinline__ void tanh4_from_exponents(const uint32_t* v, float* y) {
     float a[4];
+#if QS_TC_TANH_SAT
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float t;
+#if defined(QS_X_NOEX2)                      // timing experiments only (wrong numerics): what the XU pipe costs
+        t = __uint_as_float(v[i]) * 0.001f;
+#elif defined(QS_X_POLY)
+        if (i < QS_X_POLY) t = ex2_poly(__uint_as_float(v[i])); else
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(__uint_as_float(v[i])));
+#else
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(__uint_as_float(v[i])));
+#endif
+        asm("fma.rn.ftz.sat.f32 %0, %1, %2, %2;" : "=f"(a[i]) : "f"(t), "f"(4.656612873077393e-10f));     // 2^-31
+    }
+    const float p = a[0] * a[1], q = a[2] * a[3];
+    float r;
+#ifdef QS_X_NORCP
+    r = p * q * 0.37f;
+#else
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p * q));
+#endif
+    r *= -9.313225746154785e-10f;            // -2 s = -2^-30
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float t, u;
@@ -152,6 +198,7 @@ __device__ __forceinline__ void tanh4_from_exponents(const uint32_t* v, float* y
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p * q));
     r *= -2.0f;
+#endif
     const float rp = r * q, rq = r * p;      // -2/(a0 a1), -2/(a2 a3)
     y[0] = fmaf(rp, a[1], 1.0f);
     y[1] = fmaf(rp, a[0], 1.0f);

@@ -262,3 +262,61 @@ def test_ppo_two_processes_one_device_stay_in_lockstep():
                         "--master-port", "29533", os.path.join(root, "tools", "ppo_multi_rank_check.py")], cwd=root, capture_output=True,
                        text=True, timeout=600, env=env)
     assert r.returncode == 0 and "PPO_MULTI_RANK_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.gpu
+def test_collect_rollouts_bookkeeping_vs_sb3_restatement():
+    """OnPolicyAlgorithm.collect_rollouts semantics of QuadPPO.collect_rollouts, replayed on a twin env and recomputed in NumPy:
+    the stored (unclipped) actions clipped to the box drive the env; rewards[t] = env reward + gamma * V(terminal_observation) for
+    envs that hit the time limit only (TimeLimit.truncated), untouched otherwise; episode_starts[t] = dones of the previous step
+    (ones at the start); values[t] = V(obs[t]); advantages / returns = SB3's GAE over those buffers with V(last obs), last dones."""
+    from oracle import sb3_oracle as so
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    from rl_aerial_manipulator_b200.ppo import QuadPPO
+    n, T, gamma, lam = 384, 8, 0.995, 0.9
+    envs = []
+    for _ in range(2):
+        e = BatchedQuadEnv(n, env_version=2, precision="f32", seed=21)
+        e.reset()
+        st = e.get_state()
+        st["current_step"][: n // 3] = torch.arange(n // 3, device="cuda", dtype=torch.int32) % 6 + 1994   # truncate within the rollout (limit 2000)
+        st["y"][n // 3: n // 2, 2] = 0.13                                                             # and some crash (terminated)
+        st["y"][n // 3: n // 2, 5] = -4.0
+        e.set_state(**st)
+        envs.append(e)
+    env, twin = envs
+    ppo = QuadPPO(env, n_steps=T, batch_size=n * T, n_epochs=1, gamma=gamma, gae_lambda=lam, policy_impl="fp32", seed=3)
+    ppo._last_obs = env.obs                                  # start from the injected state instead of a fresh reset
+    obs0 = env.obs.clone()
+    ppo.collect_rollouts()
+    sd = ppo.state_dict()
+    V = lambda o: so.torch_policy_forward(sd, o)[1]
+    lo = torch.tensor([0.0, -1, -1, -1], device="cuda")
+    hi = torch.tensor([2.0, 1, 1, 1], device="cuda")
+    obs = obs0
+    prev_done = np.ones(n, np.uint8)
+    rew, starts, n_trunc, n_term = np.zeros((T, n)), np.zeros((T, n), np.uint8), 0, 0
+    for t in range(T):
+        assert torch.equal(ppo.obs[t], obs)
+        torch.testing.assert_close(ppo.values[t], V(obs), rtol=0, atol=5e-3)
+        out = twin.step(torch.minimum(torch.maximum(ppo.actions[t], lo), hi).contiguous())
+        flags = out.flags.cpu().numpy()
+        r = out.reward.double().cpu().numpy().copy()
+        trunc_only = (flags & 3) == 2
+        if trunc_only.any():
+            tv = V(out.terminal_obs[torch.from_numpy(trunc_only).cuda()]).double().cpu().numpy()
+            r[trunc_only] += gamma * tv
+        n_trunc += int(trunc_only.sum())
+        n_term += int(((flags & 1) != 0).sum())
+        rew[t], starts[t] = r, prev_done
+        prev_done = ((flags & 3) != 0).astype(np.uint8)
+        obs = out.obs.clone()
+    assert n_trunc >= n // 6 and n_term >= n // 12            # both kinds of episode end happened
+    np.testing.assert_array_equal(ppo.episode_starts.cpu().numpy(), starts)
+    np.testing.assert_allclose(ppo.rewards.cpu().numpy(), rew, rtol=1e-5, atol=5e-3)
+    last_v = V(obs).double().cpu().numpy()
+    a_np, r_np = sb3_gae(rew, ppo.values.double().cpu().numpy(), starts.astype(np.float64), last_v, prev_done, gamma, lam)
+    np.testing.assert_allclose(ppo.advantages.cpu().numpy(), a_np, rtol=1e-4, atol=2e-2)
+    np.testing.assert_allclose(ppo.returns.cpu().numpy(), r_np, rtol=1e-4, atol=2e-2)
+    env.close()
+    twin.close()

@@ -50,6 +50,10 @@ using namespace tc;
 // With more than 16 warps the launch-time register allowance is below what the env step needs: the roles then re-balance
 // registers with setmaxnreg (warpgroups of 4 warps: MMA group gives, env and epilogue groups take).
 constexpr int EPI_SPLIT = QS_RO_EPI_SPLIT, ENV_SPLIT = QS_RO_ENV_SPLIT;
+// Which of the EPI_SPLIT warps of a (slot, quadrant) takes hidden-layer chunk ch (0-3: layer 1, 4-5: layer 2) and which take the two
+// head chunks.  Three warps: (c0, c3, head 0) | (c1, head 1, c4) | (c2, c5) -- 3 / 3 / 2 chunk units per job.
+constexpr int HEAD_SPLIT = EPI_SPLIT < 2 ? EPI_SPLIT : 2;
+__host__ __device__ constexpr int chunk_owner(int ch) { return EPI_SPLIT == 3 ? (ch < 4 ? ch % 3 : (ch - 3) % 3) : ch % EPI_SPLIT; }
 constexpr int EPI_WARPS = 8 * EPI_SPLIT, ENV_WARPS = 4 * ENV_SPLIT, MMA_WARPS = 2;
 // A/B switch (QS_RO_ENV_FIRST): which role gets the low warp ids -- the schedulers favour older (lower) warps when several are
 // ready, and the env warps' few MUFU ops queue behind the epilogue warps' thousands
@@ -98,9 +102,9 @@ constexpr int ONE_BYTES = 2 * ROWS * 16;                                   // 12
 constexpr int X_LBO = ROWS * 16;                                           // K-direction stride between core matrices
 constexpr int SM_ONE = IMG_BYTES;
 constexpr int SM_X = SM_ONE + ONE_BYTES;
-constexpr int SM_OUT_MEAN = SM_X + XBUFS * X_BYTES;                        // float4[2][EPI_SPLIT][128] partial head sums
-constexpr int SM_OUT_VAL = SM_OUT_MEAN + 2 * EPI_SPLIT * ROWS * 16;        // float[2][EPI_SPLIT][128]
-constexpr int SM_TILE = SM_OUT_VAL + 2 * EPI_SPLIT * ROWS * 4;                         // float[ENV_WARPS][32 * 21]
+constexpr int SM_OUT_MEAN = SM_X + XBUFS * X_BYTES;                        // float4[2][HEAD_SPLIT][128] partial head sums
+constexpr int SM_OUT_VAL = SM_OUT_MEAN + 2 * HEAD_SPLIT * ROWS * 16;       // float[2][HEAD_SPLIT][128]
+constexpr int SM_TILE = SM_OUT_VAL + 2 * HEAD_SPLIT * ROWS * 4;                         // float[ENV_WARPS][32 * 21]
 constexpr int SM_MOM = SM_TILE + ENV_WARPS * 32 * 21 * 4;                  // double[ENV_WARPS][2 * 20]
 constexpr int SM_NORM = SM_MOM + ENV_WARPS * 40 * 8;                       // float[3][32]
 constexpr int SM_BARS = SM_NORM + 3 * 32 * 4;
@@ -506,6 +510,7 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
             if (stage == (QS_RO_DEFER_HEAD ? 1 : 2)) {
                 // ---- head of job hj: layer-3 accumulator D3 -> tanh -> partial sums against the float32 head weights
                 if (QS_RO_DEFER_HEAD ? job == 0 : !live) continue;
+                if (half >= HEAD_SPLIT) continue;                            // (with three warps the third has no head chunk)
                 const uint32_t hj = job - QS_RO_DEFER_HEAD, hpar = hj & 1u;
                 const int net = (int)(hj & 1u);
                 const uint32_t k = hj >> 1;                                  // this slot's tile counter
@@ -516,11 +521,11 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
 #pragma unroll
                 for (int j = 0; j < NACT; ++j) o[j] = half == 0 ? sC[C_BH + net * NACT + j] : 0.f;
 #pragma unroll 1
-                for (int ch = half; ch < 2; ch += EPI_SPLIT) {
+                for (int ch = half; ch < 2; ch += HEAD_SPLIT) {
                     uint32_t v[32];
                     tmem_ld32(tm + C_D3 + 32u * (uint32_t)ch, v);
                     tmem_ld_wait32(v);
-                    if (ch + EPI_SPLIT >= 2) {                               // this warp's last read of D3: layer 3 of the next job may overwrite it
+                    if (ch + HEAD_SPLIT >= 2) {                               // this warp's last read of D3: layer 3 of the next job may overwrite it
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(c.bar(B_D3FREE + slot));
@@ -544,8 +549,8 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
                     for (int j = 0; j < NACT; ++j) mean[j] = o[j];
                 } else {
                     if (!mbar_wait_bounded(c.bar(B_OUTE + slot * 4 + quad), (k & 1u) ^ 1u, role + B_OUTE + 1)) return;
-                    s_mean[(slot * EPI_SPLIT + half) * ROWS + row] = make_float4(mean[0], mean[1], mean[2], mean[3]);
-                    s_val[(slot * EPI_SPLIT + half) * ROWS + row] = o[0];
+                    s_mean[(slot * HEAD_SPLIT + half) * ROWS + row] = make_float4(mean[0], mean[1], mean[2], mean[3]);
+                    s_val[(slot * HEAD_SPLIT + half) * ROWS + row] = o[0];
                     __syncwarp();
                     if (lane == 0) mbar_arrive(c.bar(B_OUTF + slot * 4 + quad));
                 }
@@ -553,10 +558,12 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
                 // ---- E1 (first stage) or E2 of job `job`
                 if (!live) continue;
                 const bool first = stage == 0;
+                if (EPI_SPLIT == 3 && !first && half == 0) continue;         // owns no layer-2 chunk
                 if (!mbar_wait_bounded(c.bar((first ? B_D1 : B_D2) + slot), par, role + (first ? B_D1 : B_D2) + 1)) return;
                 tc_fence_after();
 #pragma unroll 1
-                for (int ch = (first ? 0 : 4) + half; ch < (first ? 4 : 6); ch += EPI_SPLIT) {
+                for (int ch = (first ? 0 : 4); ch < (first ? 4 : 6); ++ch) {
+                    if (chunk_owner(ch) != half) continue;
                     RO_TRACE(0x100000u | (ch << 12) | job);
                     chunk_tanh_split(tm + 32u * (uint32_t)ch);
                     tmem_st_wait();
@@ -721,13 +728,13 @@ __device__ __forceinline__ void role_env(const Ctx& c, const RoParams& p, int pa
         }
         if (!mbar_wait_bounded(c.bar(B_OUTF + slot * 4 + quad), k & 1u, 200 + B_OUTF + 1)) return;
         RO_TRACE(0x320000u | (uint32_t)i);
-        float4 mu = s_mean[slot * EPI_SPLIT * ROWS + row];
-        float value = s_val[slot * EPI_SPLIT * ROWS + row];
+        float4 mu = s_mean[slot * HEAD_SPLIT * ROWS + row];
+        float value = s_val[slot * HEAD_SPLIT * ROWS + row];
 #pragma unroll
-        for (int hf = 1; hf < EPI_SPLIT; ++hf) {                          // partial head sums of the other epilogue warp(s) of the row
-            const float4 m2 = s_mean[(slot * EPI_SPLIT + hf) * ROWS + row];
+        for (int hf = 1; hf < HEAD_SPLIT; ++hf) {                         // partial head sums of the other epilogue warp(s) of the row
+            const float4 m2 = s_mean[(slot * HEAD_SPLIT + hf) * ROWS + row];
             mu.x += m2.x; mu.y += m2.y; mu.z += m2.z; mu.w += m2.w;
-            value += s_val[(slot * EPI_SPLIT + hf) * ROWS + row];
+            value += s_val[(slot * HEAD_SPLIT + hf) * ROWS + row];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(c.bar(B_OUTE + slot * 4 + quad));
@@ -832,8 +839,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_kernel(const RoParams p
         for (int j = 0; j < N_BARS; ++j) {
             uint32_t count = 1u;                                                   // tcgen05.commit / one lane of one warp
             if ((j >= B_XFULL && j < B_XFULL + 3) || (j >= B_H1 && j < B_D3FREE)) count = 4u;   // one arrival per quadrant warp
-            if (j >= B_D3FREE && j < B_D3FREE + 2) count = 4u * EPI_SPLIT;          // every epilogue warp of the slot
-            if (j >= B_OUTF && j < B_OUTF + 8) count = EPI_SPLIT;
+            if (j >= B_D3FREE && j < B_D3FREE + 2) count = 4u * HEAD_SPLIT;         // every epilogue warp of the slot that reads D3
+            if (j >= B_OUTF && j < B_OUTF + 8) count = HEAD_SPLIT;
             tc::mbar_init(b + 8u * j, count);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -373,7 +373,7 @@ def run_gpu(args) -> None:
                     parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
             else:
                 # two kernels per step: tcgen05 pipeline policy kernel (normalise, forward, in-kernel Philox sampling, clip) + env step
-                if vn is not None and world > 1:
+                if vn is not None and world > 1 and not vn.env_merges:
                     parts["xchg_merge_kernel"] = lambda i: vn.update_from_moments()
                 parts["rollout_kernel<v2,policy>"] = lambda i: policy.forward_sampled(env.obs, noise_seed=args.seed, env_id_offset=rank * n,
                                                                                      norm_stats=vn.stats if vn is not None else None)
@@ -397,7 +397,8 @@ def run_gpu(args) -> None:
             # them also merges them into the running statistics, with several ranks one kernel does the all-gather (2D+1 doubles
             # per rank over NVLink peer memory) and the Chan merge (qs_xchg_merge; NCCL all-gather + merge kernel as fallback)
             vn = DeviceRunningMeanStd(env.obs_dim, dev, exchange=args.vecnorm_exchange)
-            vn.attach(env, merge=(world == 1))
+            # (the fused single-kernel rollout reduces its moments in its own last CTA: the exchange stays a separate launch there)
+            vn.attach(env, merge=(world == 1 or (vn.exchange == "peer" and args.rollout == "separate" and not args.split_exchange)))
     parts = build_parts(args.rollout)
     fused = fused_holder.get("f")
 
@@ -576,7 +577,8 @@ def run_gpu(args) -> None:
                                        + ", clipped to the action box") if policy else "uniform-random over the action box, regenerated on the device every step inside the timed region",
                            "l2": "working set per step (state pool + obs + actions) exceeds the 126 MB L2" if n * 185 > 126e6 else "working set fits L2; no flush between steps",
                            "parallelism": f"env-shard x{world}, no data-path collective",
-                           "moment_exchange": vn.exchange if vn is not None else "none"},
+                           "moment_exchange": (vn.exchange + (" (inside the kernel that finishes the step's moments: qs_step_moments_exchange)"
+                                                              if world > 1 and vn.env_merges else "")) if vn is not None else "none"},
                 "roofline": roofline, "roofline_other": roofline_other,
                 "kernels_ms": kernel_ms, "kernels_ms_sum": sum(kernel_ms.values()),
                 "extra": extras, "cpu_baseline": base,
@@ -598,6 +600,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--split-exchange", action="store_true", help="N > 1: the moment exchange as its own launch (qs_xchg_merge) instead of "
+                    "inside the kernel that finishes the step's moments (A/B)")
     ap.add_argument("--workload", default=None, choices=["rollout", "step"])
     ap.add_argument("--n-envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])

@@ -384,6 +384,13 @@ int qs_xchg_create(int device, int rank, int world, int d, qs_xchg** out, unsign
 int qs_xchg_connect(qs_xchg* x, const unsigned char* all_handles /*[world][64], rank order*/);
 int qs_xchg_merge(qs_xchg* x, double* stats, const double* local_moments, void* stream);
 int qs_xchg_failed(qs_xchg* x);   /* synchronises the device; 1 if any merge timed out */
+/* Sharded rollout: arm the env handle so that the kernel which finishes the fused observation moments of every qs_step
+ * (qs_step_moments must be armed) ALSO runs the exchange and the merge into `stats` (f64[1+2D]) in the same launch -- what a
+ * qs_xchg_merge(x, stats, moments_out) right after the step would do, one kernel boundary earlier (the step -> exchange ->
+ * policy chain of SB3's collect_rollouts ends at the slowest rank, so every boundary on it is paid in full).  All ranks arm
+ * it alike; it counts as one qs_xchg_merge per qs_step.  x == NULL disarms.  Replaces, with qs_step, VecNormalize.step_wait's
+ * obs_rms.update over the whole sharded batch (reference call site initial-implementation-v1/rl_train_vecN.py:11). */
+int qs_step_moments_exchange(qs_handle* h, qs_xchg* x, double* stats);
 int qs_xchg_destroy(qs_xchg* x);
 const char* qs_xchg_last_error(void);
 

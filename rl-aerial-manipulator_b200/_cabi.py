@@ -149,6 +149,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.qs_step_moments.argtypes = [vp, vp, vp]
     lib.qs_step_moments_merge.argtypes = [vp, vp]
     lib.qs_step_moments_merge.restype = C.c_int
+    lib.qs_step_moments_exchange.argtypes = [vp, vp, vp]
+    lib.qs_step_moments_exchange.restype = C.c_int
     lib.qs_get_state.argtypes = [vp, C.POINTER(QsStateView), vp]
     lib.qs_set_state.argtypes = [vp, C.POINTER(QsStateView), vp]
     lib.qs_reset_uniforms.argtypes = [vp, vp, vp, i64, vp, vp]

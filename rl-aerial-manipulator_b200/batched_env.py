@@ -187,7 +187,7 @@ class BatchedQuadEnv:
                                      p(self.terminal_obs), p(self.ep_return), p(self.ep_len), st), "qs_step_range")
 
     def fuse_obs_moments(self, moments: torch.Tensor | None, shift_stats: torch.Tensor | None = None,
-                         merge_stats: torch.Tensor | None = None) -> None:
+                         merge_stats: torch.Tensor | None = None, exchange=None) -> None:
         """From now on every step() also writes (n, mean[D], M2[D]) of the returned observations into `moments` (f64[1+2D]):
         the batch statistics VecNormalize needs, reduced inside the step kernel.  None switches it off.
         The kernel centres its sums on the mean already in `moments` (when its count is > 0), so seed it with the statistics
@@ -199,10 +199,19 @@ class BatchedQuadEnv:
         check(self.lib, self._h, self.lib.qs_step_moments(self._h, C.c_void_p(moments.data_ptr()) if moments is not None else None,
                                                           C.c_void_p(shift_stats.data_ptr()) if shift_stats is not None else None), "qs_step_moments")
         # merge_stats (f64[1+2D] running count/mean/var): every step() also performs RunningMeanStd.update on it (single GPU)
+        # exchange (a connected qs_xchg handle, several ranks): the kernel that finishes the moments also exchanges them with the peers
+        # and merges every rank's triplet into merge_stats (qs_step_moments_exchange)
         if moments is not None:
             assert merge_stats is None or (merge_stats.dtype == torch.float64 and merge_stats.numel() == 1 + 2 * self.obs_dim)
-            check(self.lib, self._h, self.lib.qs_step_moments_merge(self._h, C.c_void_p(merge_stats.data_ptr()) if merge_stats is not None else None),
-                  "qs_step_moments_merge")
+            if exchange is not None:
+                assert merge_stats is not None
+                check(self.lib, self._h, self.lib.qs_step_moments_merge(self._h, None), "qs_step_moments_merge")
+                check(self.lib, self._h, self.lib.qs_step_moments_exchange(self._h, exchange, C.c_void_p(merge_stats.data_ptr())),
+                      "qs_step_moments_exchange")
+            else:
+                check(self.lib, self._h, self.lib.qs_step_moments_exchange(self._h, None, None), "qs_step_moments_exchange")
+                check(self.lib, self._h, self.lib.qs_step_moments_merge(self._h, C.c_void_p(merge_stats.data_ptr()) if merge_stats is not None else None),
+                      "qs_step_moments_merge")
 
     # -- state injection / extraction (parity tests, plotting façade) ------------------------------
     def get_state(self, fields=None) -> dict[str, torch.Tensor]:

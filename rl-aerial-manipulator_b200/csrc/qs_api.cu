@@ -2,6 +2,7 @@
 // state injection/extraction.  No torch types, no C++ exceptions across the boundary.
 #include "../../include/quadsim.h"
 #include "qs_internal.cuh"
+#include "qs_exchange.cuh"
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -173,6 +174,8 @@ int qs_create(const qs_config* cfg, qs_handle** out) {
     h->mom_out = nullptr;
     h->mom_stats = nullptr;
     h->mom_merge = nullptr;
+    h->mom_xchg = nullptr;
+    h->mom_xchg_stats = nullptr;
     h->range_first = 0;
     h->range_count = 0;
     // last-CTA election counter of qs_rollout_step / qs_step_many: allocated here, not lazily, so that the first call of either may
@@ -286,13 +289,30 @@ int qs_step_moments(qs_handle* h, double* moments_out, const double* shift_stats
     }
     h->mom_out = moments_out;
     h->mom_stats = moments_out ? shift_stats : nullptr;
-    if (!moments_out) h->mom_merge = nullptr;
+    if (!moments_out) { h->mom_merge = nullptr; h->mom_xchg = nullptr; h->mom_xchg_stats = nullptr; }
+    return QS_OK;
+}
+
+int qs_step_moments_exchange(qs_handle* h, qs_xchg* x, double* stats) {
+    if (!h) { set_error(nullptr, "qs_step_moments_exchange: null handle"); return QS_EINVAL; }
+    if (!x) { h->mom_xchg = nullptr; h->mom_xchg_stats = nullptr; return QS_OK; }
+    if (!h->mom_out) { set_error(h, "qs_step_moments_exchange: arm qs_step_moments first"); return QS_EINVAL; }
+    if (!stats) { set_error(h, "qs_step_moments_exchange: null statistics"); return QS_EINVAL; }
+    if (h->mom_merge) { set_error(h, "qs_step_moments_exchange: qs_step_moments_merge is armed (the exchange does the merge)"); return QS_EINVAL; }
+    const int d = h->cfg.env_version == 2 ? 20 : 17;
+    if (x->d != d || !x->connected) {
+        set_error(h, "qs_step_moments_exchange: the exchange must be connected and have the env's observation width (%d)", d);
+        return QS_EINVAL;
+    }
+    h->mom_xchg = x;
+    h->mom_xchg_stats = stats;
     return QS_OK;
 }
 
 int qs_step_moments_merge(qs_handle* h, double* merge_stats) {
     if (!h) { set_error(nullptr, "qs_step_moments_merge: null handle"); return QS_EINVAL; }
     if (merge_stats && !h->mom_out) { set_error(h, "qs_step_moments_merge: arm qs_step_moments first"); return QS_EINVAL; }
+    if (merge_stats && h->mom_xchg) { set_error(h, "qs_step_moments_merge: qs_step_moments_exchange is armed (the exchange does the merge)"); return QS_EINVAL; }
     h->mom_merge = merge_stats;
     return QS_OK;
 }

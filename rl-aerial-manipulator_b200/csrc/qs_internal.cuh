@@ -13,6 +13,8 @@ struct qs_handle {
     double* mom_out;          // caller-owned (n, mean[D], M2[D]) triplet
     const double* mom_stats;  // caller-owned VecNormalize stats used as the shift (or null)
     double* mom_merge;        // caller-owned running statistics the batch triplet is merged into by the step (or null)
+    struct qs_xchg* mom_xchg; // several ranks: the peer-memory exchange the kernel that finishes the moments also runs (or null)
+    double* mom_xchg_stats;   // ... and the running statistics the exchanged triplets are merged into
     qs::LsodaTables* ls_tables;
     int32_t* ls_counters;
     double* ls_steps;

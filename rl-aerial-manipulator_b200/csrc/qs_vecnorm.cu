@@ -22,6 +22,7 @@
 //   returns_update   the discounted-return recursion feeding ret_rms
 #include "../../include/quadsim.h"
 #include "qs_internal.cuh"
+#include "qs_exchange.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -68,9 +69,9 @@ __global__ void moments_partial_kernel(const float* __restrict__ x, int64_t n, i
 // stats[1..d] (fused moments of the env-step kernel; x == nullptr), or zero when both are null.
 // merge != nullptr: the batch triplet is also Chan-merged into the running statistics `merge` (RunningMeanStd.update), same
 // arithmetic as vecnorm_merge_kernel with k = 1.
-__global__ void __launch_bounds__(1024) moments_final_kernel(const float* __restrict__ x, const double* __restrict__ stats,
-                                                             const double* __restrict__ partial, int blocks, int64_t n, int d,
-                                                             double* __restrict__ out /*[1+2d]*/, double* merge) {
+__device__ __forceinline__ void moments_final_body(const float* __restrict__ x, const double* __restrict__ stats,
+                                                   const double* __restrict__ partial, int blocks, int64_t n, int d,
+                                                   double* out /*[1+2d]*/, double* merge) {
     __shared__ double s[64][64];
     const int w = 2 * d, S = (1024 / w) < 64 ? (1024 / w) : 64;
     const int col = threadIdx.x % w, slice = threadIdx.x / w;
@@ -121,6 +122,23 @@ __global__ void __launch_bounds__(1024) moments_final_kernel(const float* __rest
             if (threadIdx.x == 0) merge[0] = count;
         }
     }
+}
+
+__global__ void __launch_bounds__(1024) moments_final_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                             const double* __restrict__ partial, int blocks, int64_t n, int d,
+                                                             double* __restrict__ out /*[1+2d]*/, double* merge) {
+    moments_final_body(x, stats, partial, blocks, n, d, out, merge);
+}
+// Several ranks: the same reduction, then -- in the same launch -- the peer-memory exchange of the triplet it has just written and the
+// Chan merge of every rank's triplet into the running statistics `xstats` (qs_exchange.cuh).  One kernel boundary less on the
+// step -> exchange -> policy chain of a sharded rollout, where every boundary is paid at the slowest rank.
+__global__ void __launch_bounds__(1024) moments_final_xchg_kernel(const double* __restrict__ stats, const double* __restrict__ partial, int blocks,
+                                                                  int64_t n, int d, double* out /*[1+2d]*/, void* const* __restrict__ peers,
+                                                                  int rank, int world, unsigned long long* seq, int* failed, double* xstats) {
+    moments_final_body(nullptr, stats, partial, blocks, n, d, out, nullptr);
+    __threadfence();
+    __syncthreads();                                  // the triplet is complete (and visible to the whole CTA) before it is published
+    xchg_merge_body(peers, rank, world, d, seq, failed, xstats, out);
 }
 
 __global__ void vecnorm_merge_kernel(double* __restrict__ stats, const double* __restrict__ moments, int k, int d) {
@@ -200,7 +218,13 @@ static int vn_check(cudaError_t err, const char* what) {
 
 int launch_moments_final(qs_handle* h, unsigned blocks, cudaStream_t st) {
     const int d = h->cfg.env_version == 2 ? 20 : 17;
-    moments_final_kernel<<<1, 1024, 0, st>>>(nullptr, h->mom_stats, h->mom_scratch, (int)blocks, h->cfg.n_envs, d, h->mom_out, h->mom_merge);
+    if (h->mom_xchg) {
+        const qs_xchg* x = h->mom_xchg;
+        moments_final_xchg_kernel<<<1, 1024, 0, st>>>(h->mom_stats, h->mom_scratch, (int)blocks, h->cfg.n_envs, d, h->mom_out, x->peer_dev, x->rank,
+                                                       x->world, x->seq, x->failed, h->mom_xchg_stats);
+    } else {
+        moments_final_kernel<<<1, 1024, 0, st>>>(nullptr, h->mom_stats, h->mom_scratch, (int)blocks, h->cfg.n_envs, d, h->mom_out, h->mom_merge);
+    }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error(h, "moments_final_kernel launch failed: %s", cudaGetErrorString(err));

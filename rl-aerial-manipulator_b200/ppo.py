@@ -218,7 +218,10 @@ class QuadPPO:
             self._last_obs = env.reset()
             if vn is not None and vn.norm_obs and vn.training:
                 vn.obs_rms.update(self._last_obs)                # VecNormalize.reset() updates the statistics too
-                vn.obs_rms.attach(env)                           # from here on the step kernel reduces its own observations
+                # from here on the step kernel reduces its own observations and, where one launch can do it (one GPU, or several over
+                # the peer-memory exchange), the kernel that finishes them also merges them into the running statistics
+                rms = vn.obs_rms
+                vn.obs_rms.attach(env, merge=(rms._gathered is None or rms.exchange == "peer"))
         self._ep_stats.zero_()
         for t in range(self.n_steps):
             self._noise.normal_(generator=self.gen)

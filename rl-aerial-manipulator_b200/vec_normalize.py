@@ -103,6 +103,10 @@ class DeviceRunningMeanStd:
     def close(self) -> None:
         if self._xchg:
             torch.cuda.synchronize(self.device)
+            env = getattr(self, "_env", None)
+            if env is not None and getattr(self, "env_merges", False) and getattr(env, "_h", None):
+                env.fuse_obs_moments(None)          # the env handle must not keep a pointer to the exchange
+                self._env = None
             dist.barrier(group=self.group)          # nobody unmaps while a peer may still store into the buffer
             self.lib.qs_xchg_destroy(self._xchg)
             self._xchg = None
@@ -139,13 +143,19 @@ class DeviceRunningMeanStd:
 
     def attach(self, env, merge: bool = False) -> None:
         """Let `env`'s step kernel produce the batch moments of the observations it returns (no separate read pass):
-        after every env.step(), call update_from_moments().  merge=True (single GPU only): the step also merges them into
-        these running statistics itself (qs_step_moments_merge) and update_from_moments() without argument becomes a no-op."""
-        if merge and self._gathered is not None:
-            raise ValueError("merge=True needs a single rank: with several ranks the moments are exchanged before the merge")
+        after every env.step(), call update_from_moments().  merge=True: the step also merges them into these running statistics
+        itself -- qs_step_moments_merge on one GPU, qs_step_moments_exchange (peer-memory all-gather + merge in the kernel that
+        finishes the moments) with several ranks -- and update_from_moments() without argument becomes a no-op."""
+        if merge and self._gathered is not None and not self._xchg:
+            raise ValueError("merge=True with several ranks needs the peer-memory exchange (exchange='peer'): over NCCL the all-gather "
+                             "is a separate call between the step and the merge")
         self.batch_moments(env.obs)                     # seeds the summation offset with the current observations' mean
-        env.fuse_obs_moments(self._moments, self.stats, merge_stats=self.stats if merge else None)
+        # several ranks + merge: the kernel that finishes the step's moments also runs the peer exchange and merges every rank's
+        # triplet (qs_step_moments_exchange) -- one launch for what update_from_moments() does after the step otherwise
+        env.fuse_obs_moments(self._moments, self.stats, merge_stats=self.stats if merge else None,
+                             exchange=self._xchg if (merge and self._xchg) else None)
         self.env_merges = bool(merge)
+        self._env = env
 
     def update_from_moments(self, m: torch.Tensor | None = None) -> None:
         """Merge a batch triplet (n, mean, M2) -- by default `self._moments`, e.g. filled by the env-step kernel

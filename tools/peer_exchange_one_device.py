@@ -50,6 +50,44 @@ for _ in range(64):
 torch.cuda.synchronize()
 assert torch.allclose(peer.stats.cpu(), want, rtol=1e-10, atol=1e-300) and not peer.exchange_failed()
 dist.barrier()
+# ---- the exchange inside the kernel that finishes the env step's observation moments (qs_step_moments_exchange): every step of a
+# sharded env leaves the statistics of the WHOLE batch on every rank, one launch after the step kernel -- against the oracle's merge of
+# the per-rank batch moments of the returned observations, step by step
+from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+n_env = 3000 + 96 * rank
+env = BatchedQuadEnv(n_env, env_version=2, precision="f32", seed=5, env_id_offset=4096 * rank)
+env.reset()
+rms = DeviceRunningMeanStd(D, dev, exchange="peer")
+rms.update(env.obs)
+rms.attach(env, merge=True)
+assert rms.env_merges
+ref = DeviceRunningMeanStd(D, dev, exchange="nccl")      # only its reduction pass is used (the checker side)
+ref.stats.copy_(rms.stats)
+want = rms.stats.cpu().clone()
+ga = torch.Generator(device=dev).manual_seed(7 + rank)
+lo, span = torch.tensor([0.0, -1, -1, -1], device=dev), torch.tensor([2.0, 2, 2, 2], device=dev)
+for i in range(24):
+    a = lo + span * torch.rand((n_env, 4), device=dev, generator=ga)
+    out = env.step(a)
+    rms.update_from_moments()                        # no-op: the step has merged already
+    m = ref.batch_moments(out.obs).clone()           # separate reduction pass over the same observations
+    torch.cuda.synchronize()
+    allm = [torch.empty(1 + 2 * D, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allm, m.cpu())
+    want = so.merge_moments(want, torch.stack(allm))
+    got = rms.stats.cpu()
+    # the fused moments are float32 group sums re-centred in float64 (1e-6 class against the float64 reduction pass, as on one GPU)
+    assert torch.allclose(got, want, rtol=2e-6, atol=1e-9), (i, (got - want).abs().max())
+    want = got.clone()
+assert not rms.exchange_failed()
+alls = [torch.empty(1 + 2 * D, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(alls, rms.stats.cpu())
+assert all(torch.equal(alls[0], s_) for s_ in alls)
+assert float(rms.count) > 24 * (3000 + 3096) - 1
+dist.barrier()
+rms.close()
+ref.close()
+env.close()
 if rank == 0:
     print(f"PEER_ONE_DEVICE_OK world={world} steps={STEPS + 64} count={float(peer.count):.1f}", flush=True)
 peer.close()

@@ -271,6 +271,10 @@ __device__ __forceinline__ void split_h2_rn(float a, float b, uint32_t& hi, uint
     lo = hi ^ 0x3C003C00u;
     return;
 #endif
+#ifdef QS_X_TRUNCSPLIT                       // A/B: hi by truncation (LOP3 on the ALU pipe), lo = exact remainder by FADD (r01's split)
+    split_h2(a, b, hi, lo);
+    return;
+#endif
     float la, lb;
     asm("{\n\t"
         ".reg .f16 l, h, m;\n\t"
@@ -453,8 +457,7 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t* v) {
 // eight activations of this lane's row: tanh -> hi | lo packed halves stored at hi_col / lo_col (4 columns each)
 __device__ __forceinline__ void tanh_split8(const uint32_t* v, uint32_t hi_col, uint32_t lo_col) {
     float y[8];
-    tanh4_from_exponents(v, y);
-    tanh4_from_exponents(v + 4, y + 4);
+    tanh8_from_exponents(v, y);
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split_h2_rn(y[2 * j], y[2 * j + 1], h[j], l[j]);
@@ -534,8 +537,7 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
 #pragma unroll
                     for (int sb = 0; sb < 4; ++sb) {
                         float y[8];
-                        tanh4_from_exponents(v + 8 * sb, y);
-                        tanh4_from_exponents(v + 8 * sb + 4, y + 4);
+                        tanh8_from_exponents(v + 8 * sb, y);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 w = wh[8 * sb + q];

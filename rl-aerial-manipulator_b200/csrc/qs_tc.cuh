@@ -205,6 +205,42 @@ __device__ __forceinline__ void tanh4_from_exponents(const uint32_t* v, float* y
     y[2] = fmaf(rq, a[3], 1.0f);
     y[3] = fmaf(rq, a[2], 1.0f);
 }
+// Eight tanh on one MUFU.RCP (r02): two groups of four as above, each group's product P (in [2^-124, 1]) lifted by 2^62 into
+// [2^-62, 2^62] so that the product of both stays inside [2^-124, 2^124]; 1/P_a = P_b * rcp(P_a P_b).  A MUFU costs ~4.75 issue
+// cycles in this instruction mix on B200 and an FMUL ~0.54 (profiles/r02/pipe_rates_b200.txt), so trading half a reciprocal per four
+// activations for 2.5 multiplications pays.  One more rounding than tanh4 on the way to 1/a: <= ~5e-7 absolute on tanh.
+#ifndef QS_TC_RCP8
+#define QS_TC_RCP8 1
+#endif
+__device__ __forceinline__ void tanh8_from_exponents(const uint32_t* v, float* y) {
+#if QS_TC_RCP8 && QS_TC_TANH_SAT && !defined(QS_X_NOEX2) && !defined(QS_X_POLY) && !defined(QS_X_NORCP)
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float t;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(__uint_as_float(v[i])));
+        asm("fma.rn.ftz.sat.f32 %0, %1, %2, %2;" : "=f"(a[i]) : "f"(t), "f"(4.656612873077393e-10f));     // 2^-31
+    }
+    const float p0 = a[0] * a[1], q0 = a[2] * a[3], p1 = a[4] * a[5], q1 = a[6] * a[7];
+    const float P0 = (p0 * 4.611686018427388e18f) * q0, P1 = (p1 * 4.611686018427388e18f) * q1;          // 2^62 * (a0 a1 a2 a3)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(P0 * P1));
+    const float c = -4294967296.0f;                                   // -2 s 2^62 = -2^32
+    const float i0 = (r * P1) * c, i1 = (r * P0) * c;                 // -2 s / (a0 a1 a2 a3), -2 s / (a4 a5 a6 a7)
+    const float rp0 = i0 * q0, rq0 = i0 * p0, rp1 = i1 * q1, rq1 = i1 * p1;
+    y[0] = fmaf(rp0, a[1], 1.0f);
+    y[1] = fmaf(rp0, a[0], 1.0f);
+    y[2] = fmaf(rq0, a[3], 1.0f);
+    y[3] = fmaf(rq0, a[2], 1.0f);
+    y[4] = fmaf(rp1, a[5], 1.0f);
+    y[5] = fmaf(rp1, a[4], 1.0f);
+    y[6] = fmaf(rq1, a[7], 1.0f);
+    y[7] = fmaf(rq1, a[6], 1.0f);
+#else
+    tanh4_from_exponents(v, y);
+    tanh4_from_exponents(v + 4, y + 4);
+#endif
+}
 __device__ __forceinline__ void tanh2_from_exponents(const uint32_t* v, float* y) {   // A/B variant: 3 MUFU per 2 elements
     float a[2];
 #pragma unroll

@@ -208,9 +208,10 @@ __device__ __forceinline__ void tanh4_from_exponents(const uint32_t* v, float* y
 // Eight tanh on one MUFU.RCP (r02): two groups of four as above, each group's product P (in [2^-124, 1]) lifted by 2^62 into
 // [2^-62, 2^62] so that the product of both stays inside [2^-124, 2^124]; 1/P_a = P_b * rcp(P_a P_b).  A MUFU costs ~4.75 issue
 // cycles in this instruction mix on B200 and an FMUL ~0.54 (profiles/r02/pipe_rates_b200.txt), so trading half a reciprocal per four
-// activations for 2.5 multiplications pays.  One more rounding than tanh4 on the way to 1/a: <= ~5e-7 absolute on tanh.
+// activations for 2.5 multiplications should pay -- measured: 279.3 vs 279.7 us per 1M-env launch on one box, i.e. nothing, for one
+// more rounding on the way to 1/a (<= ~6e-7 absolute on tanh instead of ~2e-7).  Off by default (QS_TC_RCP8=1 builds it).
 #ifndef QS_TC_RCP8
-#define QS_TC_RCP8 1
+#define QS_TC_RCP8 0
 #endif
 __device__ __forceinline__ void tanh8_from_exponents(const uint32_t* v, float* y) {
 #if QS_TC_RCP8 && QS_TC_TANH_SAT && !defined(QS_X_NOEX2) && !defined(QS_X_POLY) && !defined(QS_X_NORCP)

@@ -478,8 +478,30 @@ __device__ __forceinline__ void chunk_tanh_split(uint32_t col) {
 #else
     tmem_ld32(col, v);
     tmem_ld_wait32(v);
+#if QS_RO_ST16                                   // A/B: two 16-column stores per chunk (one address, no per-store R2UR) instead of eight 4-column ones
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int sb = 0; sb < 4; ++sb) {
+        float y[8];
+        tanh8_from_exponents(v + 8 * sb, y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_h2_rn(y[2 * j], y[2 * j + 1], h[4 * sb + j], l[4 * sb + j]);
+    }
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 a2;\n\t"
+        "add.u32 a2, %0, 16;\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [a2], {%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
+        "}\n" ::"r"(col),
+        "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]), "r"(h[8]), "r"(h[9]), "r"(h[10]), "r"(h[11]), "r"(h[12]),
+        "r"(h[13]), "r"(h[14]), "r"(h[15]), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]), "r"(l[8]), "r"(l[9]),
+        "r"(l[10]), "r"(l[11]), "r"(l[12]), "r"(l[13]), "r"(l[14]), "r"(l[15])
+        : "memory");
+#else
 #pragma unroll
     for (int sb = 0; sb < 4; ++sb) tanh_split8(v + 8 * sb, col + 4u * sb, col + 16u + 4u * sb);
+#endif
 #endif
 }
 
@@ -493,6 +515,19 @@ __device__ __forceinline__ void chunk_tanh_split(uint32_t col) {
 // iteration later to match (LAG in role_env).
 #ifndef QS_RO_DEFER_HEAD
 #define QS_RO_DEFER_HEAD 1
+#endif
+// QS_RO_ST16: the epilogue stores a converted chunk with two 16-column tcgen05.st from ONE address register instead of eight 4-column
+// ones (each needs its address in a uniform register: 9 R2UR + 12 register moves per chunk in the SASS).  Policy build (80 registers):
+// 275.1 -> 266.5 us per 1M-env launch; the fused build's epilogue warps (72 / 88 registers) get slower with it (378 -> 392 us).
+#ifndef QS_RO_ST16
+#ifdef QS_RO_BUILD_POLICY
+#define QS_RO_ST16 1
+#else
+#define QS_RO_ST16 0
+#endif
+#endif
+#ifndef QS_RO_HEAD_SCALAR_VF
+#define QS_RO_HEAD_SCALAR_VF 1
 #endif
 __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, int quad, int lane, const float* sC, float4* s_mean, float* s_val) {
     const uint32_t tm = c.tmem + slot * SLOT_COLS + ((uint32_t)(quad * 32) << 16);
@@ -538,10 +573,19 @@ __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, 
                     for (int sb = 0; sb < 4; ++sb) {
                         float y[8];
                         tanh8_from_exponents(v + 8 * sb, y);
+#if QS_RO_HEAD_SCALAR_VF
+                        if (net == 1) {                                      // the critic's head has ONE output: a scalar weight and one FFMA per activation
+                            const float* w1 = reinterpret_cast<const float*>(wh + 8 * sb);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 w = wh[8 * sb + q];
-                            o[0] = fmaf(y[q], w.x, o[0]); o[1] = fmaf(y[q], w.y, o[1]); o[2] = fmaf(y[q], w.z, o[2]); o[3] = fmaf(y[q], w.w, o[3]);
+                            for (int q = 0; q < 8; ++q) o[0] = fmaf(y[q], w1[4 * q], o[0]);
+                        } else
+#endif
+                        {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 w = wh[8 * sb + q];
+                                o[0] = fmaf(y[q], w.x, o[0]); o[1] = fmaf(y[q], w.y, o[1]); o[2] = fmaf(y[q], w.z, o[2]); o[3] = fmaf(y[q], w.w, o[3]);
+                            }
                         }
                     }
                 }

@@ -68,6 +68,16 @@ constexpr int EPI_WARPS = 8 * EPI_SPLIT, ENV_WARPS = 4 * ENV_SPLIT, MMA_WARPS = 
 #ifndef QS_RO_LD_SPLIT
 #define QS_RO_LD_SPLIT 0
 #endif
+// QS_RO_ST16: the epilogue stores a converted chunk with two 16-column tcgen05.st from ONE address register instead of eight 4-column
+// ones (each needs its address in a uniform register: 9 R2UR + 12 register moves per chunk in the SASS).  Policy build (80 registers):
+// 275.1 -> 266.5 us per 1M-env launch; the fused build's epilogue warps (72 / 88 registers) get slower with it (378 -> 392 us).
+#ifndef QS_RO_ST16
+#ifdef QS_RO_BUILD_POLICY
+#define QS_RO_ST16 1
+#else
+#define QS_RO_ST16 0
+#endif
+#endif
 constexpr int W_EPI0 = QS_RO_ENV_FIRST ? ENV_WARPS : 0, W_ENV0 = QS_RO_ENV_FIRST ? 0 : EPI_WARPS, W_MMA0 = EPI_WARPS + ENV_WARPS;
 // the block is padded to whole groups of 4 warps: registers are allocated per 4 warps anyway (a 448 x 144 launch is refused)
 constexpr int RO_WARPS = ((EPI_WARPS + ENV_WARPS + MMA_WARPS + 3) / 4) * 4;
@@ -515,16 +525,6 @@ __device__ __forceinline__ void chunk_tanh_split(uint32_t col) {
 // iteration later to match (LAG in role_env).
 #ifndef QS_RO_DEFER_HEAD
 #define QS_RO_DEFER_HEAD 1
-#endif
-// QS_RO_ST16: the epilogue stores a converted chunk with two 16-column tcgen05.st from ONE address register instead of eight 4-column
-// ones (each needs its address in a uniform register: 9 R2UR + 12 register moves per chunk in the SASS).  Policy build (80 registers):
-// 275.1 -> 266.5 us per 1M-env launch; the fused build's epilogue warps (72 / 88 registers) get slower with it (378 -> 392 us).
-#ifndef QS_RO_ST16
-#ifdef QS_RO_BUILD_POLICY
-#define QS_RO_ST16 1
-#else
-#define QS_RO_ST16 0
-#endif
 #endif
 #ifndef QS_RO_HEAD_SCALAR_VF
 #define QS_RO_HEAD_SCALAR_VF 1

@@ -171,7 +171,7 @@ class QuadPPO:
     def __init__(self, env, vecnorm=None, state_dict: dict | None = None, n_steps: int = 64, batch_size: int = 65536, n_epochs: int = 10,
                  gamma: float = 0.995, gae_lambda: float = 0.9, clip_range: float = 0.2, ent_coef: float = 0.01, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 2e-4, normalize_advantage: bool = True, seed: int = 0,
-                 policy_impl: str = "auto", boot_cap: int | None = None):
+                 policy_impl: str = "auto", boot_cap: int | None = None, rollout_graph: bool | None = None):
         self.env, self.vecnorm = env, vecnorm
         self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
         self.gamma, self.gae_lambda = gamma, gae_lambda
@@ -201,6 +201,14 @@ class QuadPPO:
         self._boot_overflow = torch.zeros((), dtype=torch.bool, device=dev)
         self._last_dones = torch.ones(n, dtype=torch.uint8, device=dev)
         self._last_obs = None
+        # rollout_graph: one collection step (about thirty small launches of bookkeeping around the two kernels) captured ONCE as a
+        # CUDA graph and replayed per step -- at the reference's 8 envs x 2048 steps a collection is bound by the host's launch path
+        # (profiles/r02/ppo_ref_hparams_breakdown.txt), not by the device.  None: on for a single rank.
+        self._use_graph = (self.world == 1) if rollout_graph is None else bool(rollout_graph)
+        self._graph = None
+        self._t = torch.zeros(1, dtype=torch.int64, device=dev)             # the step's slot in the rollout buffers (device: graph replays)
+        self._st_obs = torch.empty((n, d), **f32)
+        self._st_rew = torch.empty(n, **f32)
         self.num_timesteps = 0
         self._ep_stats = torch.zeros(2, dtype=torch.float64, device=dev)
         self._zero = torch.zeros((), dtype=torch.float64, device=dev)
@@ -211,6 +219,81 @@ class QuadPPO:
         stats = self.vecnorm.obs_rms.stats if (self.vecnorm is not None and self.vecnorm.norm_obs) else None
         eps, clip = (self.vecnorm.epsilon, self.vecnorm.clip_obs) if self.vecnorm is not None else (1e-8, 10.0)
         return (policy or self.policy).forward(obs_raw, noise, norm_stats=stats, norm_eps=eps, norm_clip=clip, obs_norm_out=obs_norm_out)
+
+    def _bootstrap_truncated(self, out, rew):
+        """TimeLimit.truncated: rew += gamma * V(terminal_obs) for the envs that hit the time limit only -- without a host round trip.
+        Up to 65,536 envs the critic simply runs on every env's terminal_obs row and the result is masked (rows of envs that did not
+        finish hold an older episode's terminal observation: finite, and discarded by the where); above, the truncated envs are
+        compacted into a FIXED number of slots (nonzero_static; unused slots point at env 0 and add zero), so nothing waits for a count."""
+        trunc_only = (out.flags & 3) == 2
+        if self._boot_cap >= self.env.n_envs:
+            tv = self._forward(out.terminal_obs, None, policy=self._aux)[1]
+            rew.add_(torch.where(trunc_only, self.gamma * tv, self._boot_zero))
+            return
+        cnt = trunc_only.sum()
+        idx = torch.nonzero_static(trunc_only, size=self._boot_cap, fill_value=0)[:, 0]
+        tv = self._forward(out.terminal_obs.index_select(0, idx), None, policy=self._aux)[1]
+        rew.index_add_(0, idx, torch.where(self._boot_slots < cnt, self.gamma * tv, self._boot_zero))
+        self._boot_overflow |= cnt > self._boot_cap
+
+    def _graph_step(self):
+        """One collection step with every address fixed (what _collect_eager does per step, with the slot of the rollout buffers taken
+        from the device-resident counter self._t through index_copy_): capturable, and the body of the replayed graph."""
+        env, vn = self.env, self.vecnorm
+        self._noise.normal_(generator=self.gen)
+        raw = env.obs
+        use_norm = vn is not None and vn.norm_obs
+        a, v, lp = self._forward(raw, self._noise, self._st_obs if use_norm else None)
+        t = self._t
+        self.obs.index_copy_(0, t, (self._st_obs if use_norm else raw).unsqueeze(0))
+        self.actions.index_copy_(0, t, a.unsqueeze(0))
+        self.values.index_copy_(0, t, v.unsqueeze(0))
+        self.logp.index_copy_(0, t, lp.unsqueeze(0))
+        self.episode_starts.index_copy_(0, t, self._last_dones.unsqueeze(0))
+        out = env.step(self.policy.actions_clipped)
+        if vn is not None and vn.training:
+            if vn.norm_obs:
+                vn.obs_rms.update_from_moments()
+            vn.update_returns(out)
+        if vn is not None and vn.norm_reward:
+            torch.clamp(out.reward / torch.sqrt(vn.ret_rms.var[0] + vn.epsilon), -vn.clip_reward, vn.clip_reward, out=self._st_rew)
+        else:
+            self._st_rew.copy_(out.reward)
+        self._bootstrap_truncated(out, self._st_rew)
+        self.rewards.index_copy_(0, t, self._st_rew.unsqueeze(0))
+        done = (out.flags & 3) != 0
+        self._last_dones.copy_(done)
+        self._ep_stats[0] += torch.where(done, out.ep_return.double(), self._zero).sum()
+        self._ep_stats[1] += done.sum()
+        self._t.add_(1)
+
+    def _collect_graph(self) -> bool:
+        """The n_steps of a collection as replays of one captured step.  The first two steps of the first collection run eagerly
+        (lazy initialisation must not happen under capture); they are real steps.  False: not applicable, collect eagerly."""
+        env = self.env
+        if self.n_steps < 4 or self._last_obs.data_ptr() != env.obs.data_ptr():
+            return False
+        vn = self.vecnorm
+        key = (vn is not None, bool(vn and vn.training), bool(vn and vn.norm_obs), bool(vn and vn.norm_reward), float(self.gamma), self.n_steps)
+        if self._graph is not None and self._graph[1] != key:
+            self._graph = None                                   # a setting the captured step depends on has changed
+        self._t.zero_()
+        done = 0
+        if self._graph is None:
+            for _ in range(2):
+                self._graph_step()
+            done = 2
+            torch.cuda.synchronize(env.device)
+            g = torch.cuda.CUDAGraph()
+            g.register_generator_state(self.gen)
+            with torch.cuda.graph(g):
+                self._graph_step()
+            self._graph = (g, key)
+        g = self._graph[0]
+        for _ in range(done, self.n_steps):
+            g.replay()
+        self._last_obs = env.obs
+        return True
 
     def collect_rollouts(self):
         env, vn = self.env, self.vecnorm
@@ -223,6 +306,12 @@ class QuadPPO:
                 rms = vn.obs_rms
                 vn.obs_rms.attach(env, merge=(rms._gathered is None or rms.exchange == "peer"))
         self._ep_stats.zero_()
+        if not (self._use_graph and self._collect_graph()):
+            self._collect_eager()
+        self._finish_rollout()
+
+    def _collect_eager(self):
+        env, vn = self.env, self.vecnorm
         for t in range(self.n_steps):
             self._noise.normal_(generator=self.gen)
             raw = self._last_obs
@@ -243,19 +332,15 @@ class QuadPPO:
                 torch.clamp(out.reward / torch.sqrt(vn.ret_rms.var[0] + vn.epsilon), -vn.clip_reward, vn.clip_reward, out=self.rewards[t])
             else:
                 self.rewards[t].copy_(out.reward)
-            # TimeLimit.truncated: bootstrap with gamma * V(terminal_obs) -- without a host round trip: the truncated envs are compacted
-            # into a FIXED number of slots (nonzero_static; unused slots point at env 0 and add zero), so nothing waits for a count
-            trunc_only = (out.flags & 3) == 2
-            cnt = trunc_only.sum()
-            idx = torch.nonzero_static(trunc_only, size=self._boot_cap, fill_value=0)[:, 0]
-            tv = self._forward(out.terminal_obs.index_select(0, idx), None, policy=self._aux)[1]
-            self.rewards[t].index_add_(0, idx, torch.where(self._boot_slots < cnt, self.gamma * tv, self._boot_zero))
-            self._boot_overflow |= cnt > self._boot_cap
+            self._bootstrap_truncated(out, self.rewards[t])
             done = (out.flags & 3) != 0
-            self._last_dones = done.to(torch.uint8)
+            self._last_dones.copy_(done)                            # in place: the captured step (rollout_graph) reads this buffer
             self._ep_stats[0] += torch.where(done, out.ep_return.double(), self._zero).sum()     # Monitor-style episode returns,
             self._ep_stats[1] += done.sum()                                                     # reduced on device
             self._last_obs = out.obs
+
+    def _finish_rollout(self):
+        env, vn = self.env, self.vecnorm
         last_values = self._forward(self._last_obs, None, policy=self._aux)[1]
         gae(self.rewards, self.values, self.episode_starts, last_values, self._last_dones, self.gamma, self.gae_lambda,
             out=(self.advantages, self.returns))

@@ -320,3 +320,43 @@ def test_collect_rollouts_bookkeeping_vs_sb3_restatement():
     np.testing.assert_allclose(ppo.returns.cpu().numpy(), r_np, rtol=1e-4, atol=2e-2)
     env.close()
     twin.close()
+
+
+@pytest.mark.gpu
+def test_graph_replayed_collection_equals_eager_collection():
+    """QuadPPO(rollout_graph=True) replays ONE captured collection step (fixed addresses, rollout-buffer slot from a device counter);
+    it must fill the rollout buffers exactly as the eager loop does -- same kernels, same order, same random stream -- over two
+    collections (the second one is replays only), with VecNormalize (norm_obs + norm_reward) in the loop and envs that hit the time
+    limit or crash inside the rollout."""
+    from rl_aerial_manipulator_b200.batched_env import BatchedQuadEnv
+    from rl_aerial_manipulator_b200.ppo import QuadPPO
+    from rl_aerial_manipulator_b200.vec_normalize import DeviceVecNormalize
+    n, T = 512, 12
+    runs = []
+    for use_graph in (False, True):
+        env = BatchedQuadEnv(n, env_version=2, precision="f32", seed=11)
+        env.reset()
+        st = env.get_state()
+        st["current_step"][: n // 4] = torch.arange(n // 4, device="cuda", dtype=torch.int32) % 9 + 1990      # truncations inside the rollouts
+        st["y"][n // 4: n // 3, 2] = 0.13
+        st["y"][n // 4: n // 3, 5] = -4.0                                                               # and crashes
+        env.set_state(**st)
+        vn = DeviceVecNormalize(env, norm_obs=True, norm_reward=True, gamma=0.995)
+        ppo = QuadPPO(env, vecnorm=vn, n_steps=T, batch_size=n * T, n_epochs=1, policy_impl="fp32", seed=4, rollout_graph=use_graph)
+        ppo._last_obs = env.obs
+        vn.obs_rms.update(env.obs)
+        vn.obs_rms.attach(env, merge=True)
+        snaps = []
+        for _ in range(2):
+            ppo.collect_rollouts()
+            snaps.append({k: getattr(ppo, k).clone() for k in ("obs", "actions", "values", "logp", "rewards", "episode_starts", "advantages", "returns")})
+            snaps[-1]["stats"] = vn.obs_rms.stats.clone()
+            snaps[-1]["ret_stats"] = vn.ret_rms.stats.clone()
+            snaps[-1]["ep"] = torch.tensor([ppo.ep_count, ppo.num_timesteps])
+        assert (ppo._graph is not None) == use_graph
+        runs.append(snaps)
+        env.close()
+    for a, b in zip(*runs):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    assert int(runs[0][0]["ep"][0]) > 0                              # episodes did end (time limit, crash) inside the first rollout

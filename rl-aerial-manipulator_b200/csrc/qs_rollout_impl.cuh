@@ -546,8 +546,15 @@ __device__ __forceinline__ void chunk_tanh_split(uint32_t col) {
 #ifndef QS_RO_DEFER_HEAD
 #define QS_RO_DEFER_HEAD 1
 #endif
+// QS_RO_HEAD_SCALAR_VF: the critic's head has one output -- a scalar weight and one FFMA per activation instead of the actor's float4 and
+// four.  Policy build: 280.1 -> 276.2 us; the fused build (one epilogue warp per (slot, quadrant), larger code) gets slower with the
+// second head body (374.5 -> 389.9 us): off there.
 #ifndef QS_RO_HEAD_SCALAR_VF
+#ifdef QS_RO_BUILD_POLICY
 #define QS_RO_HEAD_SCALAR_VF 1
+#else
+#define QS_RO_HEAD_SCALAR_VF 0
+#endif
 #endif
 __device__ __forceinline__ void role_epilogue(const Ctx& c, int slot, int half, int quad, int lane, const float* sC, float4* s_mean, float* s_val) {
     const uint32_t tm = c.tmem + slot * SLOT_COLS + ((uint32_t)(quad * 32) << 16);

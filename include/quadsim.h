@@ -330,6 +330,23 @@ int qs_gae(const float* rewards, const float* values, const uint8_t* episode_sta
            const uint8_t* last_dones, int T, int64_t n, float gamma, float gae_lambda, float* advantages, float* returns,
            void* stream);
 const char* qs_gae_last_error(void);
+/* RolloutBuffer.add for one collection step of all envs, with the buffer slot t (0 <= t < T) read from DEVICE memory so that a captured
+ * CUDA graph of the step can be replayed (SB3 OnPolicyAlgorithm.collect_rollouts around env.step; reference call sites
+ * initial-implementation-v1/rl_train_vecN.py:36, initial-implementation-v2/rl_train.py:56).  Time-major buffers [T, n, ...].
+ *   qs_rollout_record_pre:  obs_buf[t] = obs (f32[n,D], already normalised if VecNormalize is on), actions_buf[t] = the UNclipped
+ *     actions (f32[n,4]), values_buf[t], logp_buf[t], episode_starts_buf[t] = last_dones (u8[n]).
+ *   qs_rollout_record_post: rewards_buf[t] = reward (f32 or f64 source; if ret_var != NULL first VecNormalize.normalize_reward:
+ *     clip(reward / sqrt(ret_var[0] + epsilon), +-clip_reward)), plus gamma * terminal_values for envs whose flags say truncated and
+ *     not terminated (TimeLimit.truncated bootstrap); last_dones = terminated | truncated; ep_stats[0] += sum of ep_return over the
+ *     finished envs, ep_stats[1] += their number (f64[2], fixed summation order); *t_dev += 1.
+ *     workspace: f64[2 * QS_RECORD_MAX_BLOCKS + 1], zero before the first call. */
+#define QS_RECORD_MAX_BLOCKS 1024
+int qs_rollout_record_pre(const long long* t_dev, int64_t n, int obs_dim, const float* obs, const float* actions, const float* values,
+                          const float* logp, const uint8_t* last_dones, float* obs_buf, float* actions_buf, float* values_buf,
+                          float* logp_buf, uint8_t* episode_starts_buf, void* stream);
+int qs_rollout_record_post(long long* t_dev, int64_t n, const void* reward, int reward_is_f64, const uint8_t* flags, const void* ep_return,
+                           const float* terminal_values, float gamma, const double* ret_var, double epsilon, float clip_reward,
+                           float* rewards_buf, uint8_t* last_dones, double* ep_stats, double* workspace, void* stream);
 
 /* PPO minibatch update -----------------------------------------------------------------------------------
  * Replaces one minibatch of stable_baselines3 PPO.train() (inside model.learn(); reference call sites

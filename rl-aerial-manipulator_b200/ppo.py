@@ -34,6 +34,10 @@ def _bind(lib):
     vp = C.c_void_p
     lib.qs_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_float, C.c_float, vp, vp, vp]
     lib.qs_gae.restype = C.c_int
+    lib.qs_rollout_record_pre.argtypes = [vp, C.c_int64, C.c_int] + [vp] * 10 + [vp]
+    lib.qs_rollout_record_pre.restype = C.c_int
+    lib.qs_rollout_record_post.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp, vp, C.c_float, vp, C.c_double, C.c_float, vp, vp, vp, vp, vp]
+    lib.qs_rollout_record_post.restype = C.c_int
     lib.qs_gae_last_error.restype = C.c_char_p
     lib._gae_bound = True
 
@@ -209,6 +213,7 @@ class QuadPPO:
         self._t = torch.zeros(1, dtype=torch.int64, device=dev)             # the step's slot in the rollout buffers (device: graph replays)
         self._st_obs = torch.empty((n, d), **f32)
         self._st_rew = torch.empty(n, **f32)
+        self._rec_ws = torch.zeros(2 * 1024 + 1, dtype=torch.float64, device=dev)   # qs_rollout_record_post workspace (QS_RECORD_MAX_BLOCKS)
         self.num_timesteps = 0
         self._ep_stats = torch.zeros(2, dtype=torch.float64, device=dev)
         self._zero = torch.zeros((), dtype=torch.float64, device=dev)
@@ -244,6 +249,8 @@ class QuadPPO:
         raw = env.obs
         use_norm = vn is not None and vn.norm_obs
         a, v, lp = self._forward(raw, self._noise, self._st_obs if use_norm else None)
+        if self._boot_cap >= env.n_envs:
+            return self._graph_step_kernels(raw, use_norm, a, v, lp)
         t = self._t
         self.obs.index_copy_(0, t, (self._st_obs if use_norm else raw).unsqueeze(0))
         self.actions.index_copy_(0, t, a.unsqueeze(0))
@@ -266,6 +273,34 @@ class QuadPPO:
         self._ep_stats[0] += torch.where(done, out.ep_return.double(), self._zero).sum()
         self._ep_stats[1] += done.sum()
         self._t.add_(1)
+
+    def _graph_step_kernels(self, raw, use_norm, a, v, lp):
+        """The rest of _graph_step with the bookkeeping in two kernels (qs_rollout_record_pre / _post: RolloutBuffer.add, reward
+        normalisation, time-limit bootstrap, last dones, episode statistics, slot counter) instead of ~25 small torch launches; the
+        critic runs on every env's terminal_obs row (shards up to 65,536 envs).  Same float32 arithmetic as the torch expressions."""
+        env, vn = self.env, self.vecnorm
+        lib = load_library()
+        _bind(lib)
+        p = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None
+        st = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+        n = env.n_envs
+        rc = lib.qs_rollout_record_pre(p(self._t), n, env.obs_dim, p(self._st_obs if use_norm else raw), p(a), p(v), p(lp), p(self._last_dones),
+                                       p(self.obs), p(self.actions), p(self.values), p(self.logp), p(self.episode_starts), st)
+        if rc != 0:
+            raise RuntimeError(f"qs_rollout_record_pre failed ({rc}): {lib.qs_gae_last_error().decode()}")
+        out = env.step(self.policy.actions_clipped)
+        if vn is not None and vn.training:
+            if vn.norm_obs:
+                vn.obs_rms.update_from_moments()
+            vn.update_returns(out)
+        tv = self._forward(out.terminal_obs, None, policy=self._aux)[1]
+        norm_r = vn is not None and vn.norm_reward
+        rc = lib.qs_rollout_record_post(p(self._t), n, p(out.reward), int(out.reward.dtype == torch.float64), p(out.flags), p(out.ep_return), p(tv),
+                                        float(self.gamma), C.c_void_p(vn.ret_rms.stats.data_ptr() + 16) if norm_r else None,
+                                        float(vn.epsilon) if norm_r else 0.0, float(vn.clip_reward) if norm_r else 0.0, p(self.rewards),
+                                        p(self._last_dones), p(self._ep_stats), p(self._rec_ws), st)
+        if rc != 0:
+            raise RuntimeError(f"qs_rollout_record_post failed ({rc}): {lib.qs_gae_last_error().decode()}")
 
     def _collect_graph(self) -> bool:
         """The n_steps of a collection as replays of one captured step.  The first two steps of the first collection run eagerly

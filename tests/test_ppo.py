@@ -360,3 +360,63 @@ def test_graph_replayed_collection_equals_eager_collection():
         for k in a:
             assert torch.equal(a[k], b[k]), k
     assert int(runs[0][0]["ep"][0]) > 0                              # episodes did end (time limit, crash) inside the first rollout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("f64", [False, True])
+def test_rollout_record_kernels_vs_numpy(f64):
+    """qs_rollout_record_pre / _post against a NumPy restatement of RolloutBuffer.add + the reward bookkeeping of collect_rollouts
+    (reward normalisation in float32, gamma * V(terminal obs) for TimeLimit.truncated envs only, last dones, episode statistics),
+    float32 and float64 env outputs, ragged n, slot t taken from device memory and advanced by the post kernel."""
+    import ctypes as C
+    from rl_aerial_manipulator_b200 import ppo as ppo_mod
+    from rl_aerial_manipulator_b200._cabi import load_library
+    lib = load_library()
+    ppo_mod._bind(lib)
+    rng = np.random.default_rng(3)
+    n, d, T = 1000 + 37, 20, 5
+    dev = "cuda"
+    real = np.float64 if f64 else np.float32
+    t_dev = torch.tensor([2], dtype=torch.int64, device=dev)
+    bufs = {k: torch.full(shp, -7.0, dtype=torch.float32, device=dev) for k, shp in
+            (("obs", (T, n, d)), ("act", (T, n, 4)), ("val", (T, n)), ("logp", (T, n)), ("rew", (T, n)))}
+    starts = torch.full((T, n), 9, dtype=torch.uint8, device=dev)
+    last_dones = torch.from_numpy(rng.integers(0, 2, n).astype(np.uint8)).to(dev)
+    obs, act = rng.standard_normal((n, d)).astype(np.float32), rng.standard_normal((n, 4)).astype(np.float32)
+    val, logp = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    g = lambda a: torch.from_numpy(a).to(dev)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    d_obs, d_act, d_val, d_logp = g(obs), g(act), g(val), g(logp)
+    ld0 = last_dones.cpu().numpy().copy()
+    assert lib.qs_rollout_record_pre(p(t_dev), n, d, p(d_obs), p(d_act), p(d_val), p(d_logp), p(last_dones), p(bufs["obs"]), p(bufs["act"]),
+                                     p(bufs["val"]), p(bufs["logp"]), p(starts), None) == 0
+    reward = (rng.standard_normal(n) * 30).astype(real)
+    flags = rng.choice(np.array([0, 0, 0, 1, 2, 3, 0x12, 0x21], np.uint8), n)
+    ep_ret = (rng.standard_normal(n) * 1000).astype(real)
+    tv = (rng.standard_normal(n) * 50).astype(np.float32)
+    ret_stats = torch.tensor([100.0, 3.0, 412.7], dtype=torch.float64, device=dev)
+    ep_stats = torch.tensor([5.5, 2.0], dtype=torch.float64, device=dev)
+    ws = torch.zeros(2 * 1024 + 1, dtype=torch.float64, device=dev)
+    gamma, eps, clip = 0.995, 1e-8, 10.0
+    d_rew, d_flags, d_ep, d_tv = g(reward), g(flags), g(ep_ret), g(tv)
+    for use_norm in (True, False):
+        t_before = int(t_dev.item())
+        assert lib.qs_rollout_record_post(p(t_dev), n, p(d_rew), int(f64), p(d_flags), p(d_ep), p(d_tv), gamma,
+                                          C.c_void_p(ret_stats.data_ptr() + 16) if use_norm else None, eps, clip, p(bufs["rew"]), p(last_dones),
+                                          p(ep_stats), p(ws), None) == 0
+        torch.cuda.synchronize()
+        r = reward.astype(np.float32)
+        if use_norm:
+            r = np.clip(r / np.float32(np.sqrt(412.7 + eps)), np.float32(-clip), np.float32(clip))
+        f3 = flags & 3
+        r = np.where(f3 == 2, r + np.float32(gamma) * tv, r).astype(np.float32)
+        np.testing.assert_array_equal(bufs["rew"][t_before].cpu().numpy(), r)
+        assert int(t_dev.item()) == t_before + 1
+    np.testing.assert_array_equal(last_dones.cpu().numpy(), (f3 != 0).astype(np.uint8))
+    want = np.array([5.5 + 2 * ep_ret[f3 != 0].astype(np.float64).sum(), 2.0 + 2 * (f3 != 0).sum()])
+    np.testing.assert_allclose(ep_stats.cpu().numpy(), want, rtol=1e-12)
+    for k, a in (("obs", obs), ("act", act), ("val", val), ("logp", logp)):
+        np.testing.assert_array_equal(bufs[k][2].cpu().numpy(), a)
+        assert float(bufs[k][1].max()) == -7.0 and float(bufs[k][3].min()) == -7.0          # the neighbouring slots are untouched
+    np.testing.assert_array_equal(starts[2].cpu().numpy(), ld0)
+    assert int(starts[1].min()) == 9 and float(bufs["rew"][4].max()) == -7.0

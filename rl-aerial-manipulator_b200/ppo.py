@@ -319,10 +319,20 @@ class QuadPPO:
                 self._graph_step()
             done = 2
             torch.cuda.synchronize(env.device)
-            g = torch.cuda.CUDAGraph()
-            g.register_generator_state(self.gen)
-            with torch.cuda.graph(g):
-                self._graph_step()
+            try:
+                g = torch.cuda.CUDAGraph()
+                g.register_generator_state(self.gen)
+                with torch.cuda.graph(g):
+                    self._graph_step()
+            except Exception as exc:  # noqa: BLE001 -- a launch-mode optimisation only: the same step body goes on eagerly
+                import warnings
+                warnings.warn(f"QuadPPO: the collection step could not be captured as a CUDA graph ({exc}); collecting eagerly")
+                torch.cuda.synchronize(env.device)
+                self._use_graph = False
+                for _ in range(done, self.n_steps):
+                    self._graph_step()
+                self._last_obs = env.obs
+                return True
             self._graph = (g, key)
         g = self._graph[0]
         for _ in range(done, self.n_steps):

@@ -17,8 +17,8 @@ env.reset()
 rms = DeviceRunningMeanStd(20, "cuda")
 rms.update(env.obs)
 pol = MlpPolicyKernel.from_npz(os.path.join(ROOT, "tests", "golden", "policy_v2.npz"), device="cuda", impl="tensor_pipeline")
-fn = lambda: pol.forward(env.obs, None, norm_stats=rms.stats, sample="philox") if False else pol.forward(env.obs, noise, norm_stats=rms.stats)
 noise = torch.randn((n, 4), device="cuda")
+fn = lambda: pol.forward(env.obs, noise, norm_stats=rms.stats)
 for _ in range(8):
     fn()
 torch.cuda.synchronize()

@@ -297,10 +297,13 @@ def step_extra(n, precision, integrator, dev, seed, steps):
     span = torch.tensor([2.0, 2, 2, 2], device=dev)
     u, a = torch.empty((n, 4), device=dev), torch.empty((n, 4), device=dev)
     many = integrator == "rk4"          # T steps per launch, actions drawn in the kernel (qs_step_many); LSODA: one launch per step
-    T = 16 if n <= (1 << 18) else 4     # small batches: the launch is the floor; 1M envs: 4 steps keep the [T, n, ...] record at 0.4 GB
+    # small batches: launch, state round trip and the ramp of a 14-warp-per-SM wave are the floor -- 128 steps per launch (a rollout of the
+    # reference's n_steps = 2048 is 16 launches; T = 16 / 32 / 64 / 128 measured 4.01 / 3.77 / 3.61 / 3.38 us per step at 65,536 envs);
+    # 1M envs: 4 steps keep the [T, n, ...] record at 0.4 GB
+    T = int(os.environ.get("QS_BENCH_T", "0")) or (128 if n <= (1 << 18) else 4)
     if many:
         # T steps per launch, state in registers, uniform actions drawn in the kernel (Philox on (seed, global env id, step))
-        ms, graph = graph_time(lambda i: env.step_many(T, update_obs=False), max(1, steps // T), 1, dev)
+        ms, graph = graph_time(lambda i: env.step_many(T, update_obs=False), max(8, steps // T), 1, dev)
         ms /= T
         launches, actions = 1.0 / T, f"in-kernel Philox uniform over the action box, {T} steps per launch (qs_step_many)"
     else:
